@@ -1,0 +1,257 @@
+/* dpcu.h - C ABI of the B200-native culling backend (libdpcu.so)
+ *
+ * This is the drop-in boundary for nvpro-pipeline's data-parallel culling hot path.  Host code
+ * (the C++ dp::culling::cuda::Manager in pipeline_b200/dp/culling/cuda, or any other FFI
+ * client) calls ONLY these functions; nothing above this line knows about CUDA types and
+ * nothing below it knows about dp:: types.  Every entry point names the reference interface
+ * it replaces as path:line relative to the reference tree.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 (DPCU_OK) on success, otherwise a DPCU_ERR_* code
+ *     or, for CUDA runtime failures, the positive cudaError_t value.  dpcuGetLastError() returns
+ *     a thread-local, human readable message for the last failure on the calling thread.  The
+ *     C++ layer turns non-zero into std::runtime_error exactly like CUDA_VERIFY does
+ *     (dp/cuda/Config.h:47-57).
+ *   - matrices are 16 consecutive floats, row-major, row-vector convention
+ *     (dp/math/Matmnt.h:1371-1379); a "float4 array" is n * 4 floats, 16-byte aligned.
+ *   - visibility bitsets use the reference layout: object i -> u32 word i/32, bit i%32, unused
+ *     tail bits 0 (dp/util/BitArray.h:215-219,298-308).
+ *   - memspace says where a caller pointer lives: DPCU_MEM_HOST (pageable or pinned host
+ *     memory; the call copies before returning, so borrowed pointers may be released after
+ *     the call exactly as with GroupBitSet::setMatrices + cull, dp/culling/src/GroupBitSet.cpp:121-135)
+ *     or DPCU_MEM_DEVICE (memory of the context's device; copied device-to-device).
+ *   - there is NO CPU fallback: every entry point fails with DPCU_ERR_NO_DEVICE when no CUDA
+ *     device is usable.
+ *   - a context is single-threaded like the reference Manager (SURVEY.md 8b "Threading"); use
+ *     one context per thread or serialise externally.
+ */
+#ifndef DPCU_H
+#define DPCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPCU_OK                 0
+#define DPCU_ERR_INVALID_VALUE  (-1)   /* bad argument (null handle, index out of range, size mismatch) */
+#define DPCU_ERR_NO_DEVICE      (-2)   /* no usable CUDA device: there is no CPU fallback               */
+#define DPCU_ERR_OUT_OF_MEMORY  (-3)
+#define DPCU_ERR_NOT_READY      (-4)
+#define DPCU_ERR_UNSUPPORTED    (-5)
+
+#define DPCU_MEM_HOST    0
+#define DPCU_MEM_DEVICE  1
+
+#define DPCU_MAX_VIEWS   8             /* views handled by one pass over the objects */
+
+const char *dpcuGetLastError(void);
+/* library version, e.g. 0x00010000 */
+int dpcuGetVersion(void);
+
+/* ===================================================================== dp/cuda layer
+ * Thin C equivalents of the host RAII wrappers in dp/cuda (Buffer, BufferHost, Stream, Event,
+ * Device).  GL interop (GraphicsResource) and pitched 3-D buffers (Buffer3D) are not needed by
+ * the culling path and are not provided. */
+typedef struct dpcuBuffer     dpcuBuffer;      /* dp::cuda::Buffer      dp/cuda/Buffer.h:39-76         */
+typedef struct dpcuHostBuffer dpcuHostBuffer;  /* dp::cuda::BufferHost  dp/cuda/BufferHost.h:38-60     */
+typedef struct dpcuStream     dpcuStream;      /* dp::cuda::Stream      dp/cuda/Stream.h:38-62         */
+typedef struct dpcuEvent      dpcuEvent;       /* dp::cuda::Event       dp/cuda/Event.h:38-64          */
+
+/* dp::cuda::Device (dp/cuda/Device.h:39-60, src/Device.cpp).  Unlike the reference's Device
+ * destructor nothing here ever calls cudaDeviceReset. */
+int dpcuDeviceCount(int *count);
+int dpcuDeviceSelect(int device);
+int dpcuDeviceCurrent(int *device);
+int dpcuDeviceSynchronize(void);
+/* name: caller buffer of nameBytes; any out pointer may be NULL */
+int dpcuDeviceInfo(int device, char *name, size_t nameBytes, int *smCount, size_t *globalMemBytes,
+                   int *ccMajor, int *ccMinor);
+
+/* dp::cuda::Buffer::create / ~Buffer / setData / getData / fill (dp/cuda/src/Buffer.cpp) */
+int dpcuBufferCreate(dpcuBuffer **out, size_t bytes);
+int dpcuBufferDestroy(dpcuBuffer *buffer);
+int dpcuBufferSize(const dpcuBuffer *buffer, size_t *bytes);
+int dpcuBufferDevicePointer(const dpcuBuffer *buffer, void **devicePointer);
+/* stream may be NULL: synchronous copy, like the reference's setData(void const*, size_t) */
+int dpcuBufferUpload(dpcuBuffer *buffer, size_t offset, const void *host, size_t bytes, dpcuStream *stream);
+int dpcuBufferDownload(const dpcuBuffer *buffer, size_t offset, void *host, size_t bytes, dpcuStream *stream);
+int dpcuBufferFill(dpcuBuffer *buffer, int byteValue, size_t bytes, size_t offset);
+
+/* dp::cuda::BufferHost::create (pinned, optionally mapped/portable; dp/cuda/src/BufferHost.cpp) */
+#define DPCU_HOST_DEFAULT   0u
+#define DPCU_HOST_PORTABLE  1u
+#define DPCU_HOST_MAPPED    2u
+#define DPCU_HOST_WRITECOMBINED 4u
+int dpcuHostBufferCreate(dpcuHostBuffer **out, size_t bytes, unsigned flags);
+int dpcuHostBufferDestroy(dpcuHostBuffer *buffer);
+int dpcuHostBufferPointer(const dpcuHostBuffer *buffer, void **hostPointer);
+int dpcuHostBufferSize(const dpcuHostBuffer *buffer, size_t *bytes);
+
+/* dp::cuda::Stream (dp/cuda/src/Stream.cpp): blocking flag, priority, synchronize, wait(event) */
+int dpcuStreamCreate(dpcuStream **out, int blocking, int priority);
+int dpcuStreamDestroy(dpcuStream *stream);
+int dpcuStreamSynchronize(dpcuStream *stream);
+int dpcuStreamIsCompleted(dpcuStream *stream, int *completed);
+int dpcuStreamWaitEvent(dpcuStream *stream, dpcuEvent *event);
+/* raw cudaStream_t for interop (e.g. torch.cuda.ExternalStream) */
+int dpcuStreamNative(dpcuStream *stream, void **cudaStream);
+
+/* dp::cuda::Event (dp/cuda/src/Event.cpp) and getElapsedTime (dp/cuda/Event.h:62) */
+#define DPCU_EVENT_DEFAULT         0u
+#define DPCU_EVENT_BLOCKING_SYNC   1u
+#define DPCU_EVENT_DISABLE_TIMING  2u
+int dpcuEventCreate(dpcuEvent **out, unsigned flags);
+int dpcuEventDestroy(dpcuEvent *event);
+int dpcuEventRecord(dpcuEvent *event, dpcuStream *stream);
+int dpcuEventSynchronize(dpcuEvent *event);
+int dpcuEventIsCompleted(dpcuEvent *event, int *completed);
+int dpcuEventElapsedMs(dpcuEvent *start, dpcuEvent *stop, float *milliseconds);
+
+/* ===================================================================== culling layer
+ * One dpcuCull is the device mirror of one culling group (dp::culling::GroupBitSet,
+ * dp/culling/GroupBitSet.h:40-104): the object array as SoA float4 streams plus the world
+ * matrices.  One dpcuCullResult is the device mirror of one ResultBitSet
+ * (dp/culling/ResultBitSet.h:38-76): visibility bits of the previous cull plus the list of
+ * objects whose visibility changed in the last cull. */
+typedef struct dpcuCull       dpcuCull;
+typedef struct dpcuCullResult dpcuCullResult;
+
+/* replaces cpu::Manager::create + groupCreate (dp/culling/cpu/src/ManagerImpl.cpp:171-189) */
+int dpcuCullCreate(dpcuCull **out, int device);
+int dpcuCullDestroy(dpcuCull *ctx);
+
+/* Replace the whole object array (the m_inputChanged upload, dp/culling/opengl/src/GroupImpl.cpp:75-113;
+ * values as produced by ManagerBitSet::objectSetBoundingBox / objectSetTransformIndex,
+ * dp/culling/src/ManagerBitSet.cpp:88-109):
+ *   lower4[i]  = (box.lower.xyz, ignored)      extent4[i] = (box.upper - box.lower, ignored)
+ *   transformIndex[i] = index into the matrix array; may be NULL when memspace is DEVICE and
+ *   lower4[i].w already holds the index as raw u32 bits (the packed device layout).
+ * Object i of this array is group index i.  n may be 0. */
+int dpcuCullSetObjects(dpcuCull *ctx, const float *lower4, const float *extent4,
+                       const uint32_t *transformIndex, size_t n, int memspace);
+/* overwrite objects [first, first+count) of the current array (objectSetBoundingBox on live objects) */
+int dpcuCullSetObjectRange(dpcuCull *ctx, size_t first, size_t count, const float *lower4,
+                           const float *extent4, const uint32_t *transformIndex, int memspace);
+int dpcuCullGetObjectCount(const dpcuCull *ctx, size_t *n);
+
+/* groupSetMatrices (dp/culling/src/GroupBitSet.cpp:121-135): copy `count` matrices laid out with
+ * `strideBytes` between them (>= 64, multiple of 4) into the context.  The pointer is not retained. */
+int dpcuCullSetMatrices(dpcuCull *ctx, const void *matrices, size_t count, size_t strideBytes, int memspace);
+/* groupMatrixChanged (dp/culling/GroupBitSet.h:140-150) for a batch: re-read matrices[indices[k]]
+ * (same base/stride addressing as above) for k < n; indices >= the current matrix count are
+ * ignored like markMatrixDirty does.  memspace describes `matrices`; `indices` is host memory. */
+int dpcuCullUpdateMatrices(dpcuCull *ctx, const uint32_t *indices, size_t n, const void *matrices,
+                           size_t strideBytes, int memspace);
+/* Zero-copy feed: cull straight out of a device matrix array owned by someone else, e.g. the
+ * world matrices of a dpcuTree (SURVEY.md section 7 hard part 4).  64-byte stride.  The memory
+ * must stay valid until the context is rebound, given its own copy, or destroyed. */
+int dpcuCullBindMatrices(dpcuCull *ctx, const void *deviceMatrices, size_t count);
+int dpcuCullGetMatrixCount(const dpcuCull *ctx, size_t *count);
+
+/* groupCreateResult (dp/culling/cpu/src/ManagerImpl.cpp:191-194) */
+int dpcuCullResultCreate(dpcuCull *ctx, dpcuCullResult **out);
+int dpcuCullResultDestroy(dpcuCullResult *result);
+
+/* Manager::cull (dp/culling/cpu/src/ManagerImpl.cpp:467-518 + ResultBitSet::updateChanged,
+ * dp/culling/src/ResultBitSet.cpp:61-108) for nViews results at once: one pass over the objects,
+ * view v tested against viewProjections[16*v .. 16*v+16) and recorded in results[v].
+ * 1 <= nViews <= DPCU_MAX_VIEWS, results distinct and created from ctx.  On the first cull of a
+ * result, and after the object count changed, bits of new objects start as 1 (visible) exactly
+ * like ResultBitSet.cpp:65-79, so the first changed list is the set of invisible objects.
+ * Asynchronous on `stream` (NULL = the context's own stream); the result getters synchronise. */
+int dpcuCullRun(dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections,
+                int nViews, dpcuStream *stream);
+
+/* visibility words of the last cull, nWords >= ceil(n/32) */
+int dpcuCullResultGetBits(dpcuCullResult *result, uint32_t *hostWords, size_t nWords);
+/* resultGetChanged (dp/culling/src/ManagerBitSet.cpp:141-144): group indices whose visibility
+ * changed in the last cull, ASCENDING (BitArray::traverseBits order, dp/util/BitArray.h:127-136) */
+int dpcuCullResultGetChangedCount(dpcuCullResult *result, size_t *count);
+int dpcuCullResultGetChanged(dpcuCullResult *result, uint32_t *hostIndices, size_t capacity, size_t *count);
+/* resultObjectIsVisible (dp/culling/ResultBitSet.h:69-76): true when index >= result size */
+int dpcuCullResultIsVisible(dpcuCullResult *result, size_t groupIndex, int *visible);
+/* ResultBitSet::onNotify (dp/culling/src/ResultBitSet.cpp:110-128): the group moved an object
+ * from oldIndex to newIndex (GroupBitSet::removeObject, dp/culling/src/GroupBitSet.cpp:93-119) */
+int dpcuCullResultMoveBit(dpcuCullResult *result, size_t oldIndex, size_t newIndex);
+/* device-resident outputs for consumers that stay on the GPU and for the
+ * multi-GPU gather.  *changedCount points at one u32. Valid until the next run / destroy. */
+int dpcuCullResultDevicePointers(dpcuCullResult *result, const uint32_t **bits, size_t *nWords,
+                                 const uint32_t **changedIndices, const uint32_t **changedCount);
+
+/* ManagerBitSet::getBoundingBox / calculateBoundingBox, scalar branch
+ * (dp/culling/src/ManagerBitSet.cpp:151-162,268-306): out6 = lower.xyz, upper.xyz */
+int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
+
+/* Tuning / reporting knobs (never change results unless stated). */
+#define DPCU_CULL_OPT_KERNEL        1   /* 0 = auto, 1 = direct 16-byte loads, 2 = TMA-staged pipeline      */
+#define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
+#define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
+#define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */
+int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
+int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int dpcuCullGetLaunchCount(const dpcuCull *ctx, uint64_t *launches);
+
+/* ===================================================================== multi-GPU
+ * Objects shard as contiguous slices: each GPU owns one dpcuCull over its slice.
+ * When the consumer needs the full bitset on every GPU the cull kernel itself stores each
+ * finished word into every peer's buffer over NVLink (peer-mapped stores) - the all-gather is
+ * the kernel's epilogue, no separate collective is launched.
+ *   peerBits[p] : device pointer (valid on ctx's device: cudaIpc-opened or peer-enabled) to
+ *                 rank p's FULL bitset of this view, nPeers entries; entry == NULL is skipped
+ *                 (use NULL for the local rank if the local result buffer is not the full one).
+ *   wordOffset  : word index of this shard's first object inside the full bitset
+ *                 (shard starts are multiples of 1024 objects). */
+int dpcuCullResultSetPeerBits(dpcuCullResult *result, uint32_t *const *peerBits, int nPeers, size_t wordOffset);
+/* cudaIpc plumbing so one-process-per-GPU launchers (torchrun) can exchange buffers */
+#define DPCU_IPC_HANDLE_BYTES 64
+int dpcuIpcGetHandle(const void *devicePointer, unsigned char handle[DPCU_IPC_HANDLE_BYTES]);
+int dpcuIpcOpen(const unsigned char handle[DPCU_IPC_HANDLE_BYTES], void **devicePointer);
+int dpcuIpcClose(void *devicePointer);
+/* single-process multi-device launchers: enable direct access device -> peer */
+int dpcuDeviceEnablePeerAccess(int device, int peer);
+
+/* ===================================================================== transform layer
+ * Device mirror of dp::transform::Tree (dp/transform/Tree.h:40-131): local and world matrices
+ * resident in HBM, level-sorted {parent, transform} lists, dirty bit arrays; compute()
+ * propagates world = local * world[parent] level by level for dirty nodes
+ * (dp/transform/src/Tree.cpp:133-166). */
+typedef struct dpcuTree dpcuTree;
+int dpcuTreeCreate(dpcuTree **out, int device);
+int dpcuTreeDestroy(dpcuTree *tree);
+/* Topology as Tree keeps it (Tree.h:113-128): entries = {parent, transform} u32 pairs of all
+ * levels back to back; level l = entries[levelOffsets[l] .. levelOffsets[l+1]).  numNodes counts
+ * index 0, the virtual identity root (Tree.cpp:42-47).  Replaces repeated addTransform /
+ * removeTransform (Tree.cpp:54-98): the host keeps the index allocator, the device gets the lists.
+ * New nodes start with identity local/world and dirty local bit set (Tree.cpp:63). */
+int dpcuTreeSetTopology(dpcuTree *tree, const uint32_t *entries, const uint32_t *levelOffsets,
+                        int numLevels, size_t numNodes);
+/* updateLocalMatrix (Tree.h:85) for a contiguous range / a scattered batch; marks them dirty */
+int dpcuTreeSetLocals(dpcuTree *tree, size_t first, size_t count, const float *matrices, int memspace);
+int dpcuTreeUpdateLocals(dpcuTree *tree, const uint32_t *indices, size_t n, const float *matrices, int memspace);
+/* mark [first, first+count) dirty without uploading (locals were written on the device) */
+int dpcuTreeMarkDirty(dpcuTree *tree, size_t first, size_t count);
+/* Tree::compute (Tree.cpp:133-166).  Afterwards the dirty-world set of this compute is
+ * readable (the EventWorldMatricesChanged payload, Tree.h:46-58) until the next compute. */
+int dpcuTreeCompute(dpcuTree *tree, dpcuStream *stream);
+/* getWorldMatrices (Tree.h:82) - device pointer for dpcuCullBindMatrices, and host copies */
+int dpcuTreeWorldDevicePointer(dpcuTree *tree, const float **deviceMatrices, size_t *numNodes);
+int dpcuTreeLocalDevicePointer(dpcuTree *tree, float **deviceMatrices, size_t *numNodes);
+int dpcuTreeGetWorld(dpcuTree *tree, size_t first, size_t count, float *hostMatrices);
+int dpcuTreeGetDirtyWorld(dpcuTree *tree, uint32_t *hostWords, size_t nWords);
+int dpcuTreeGetLaunchCount(const dpcuTree *tree, uint64_t *launches);
+
+/* ===================================================================== synthetic scenes (bench only)
+ * On-device replay of pipeline_b200/scenes.py::random_objects: fills packed
+ * lower4 (w = global object index - indexBase as u32 bits), extent4 and matrices for objects
+ * [first, first+count).  Bit-identical to the host generator (tests/test_scene_gen.py). */
+int dpcuSceneGenerate(uint64_t seed, uint64_t first, size_t count, uint32_t indexBase,
+                      float *lower4Device, float *extent4Device, float *matricesDevice, dpcuStream *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPCU_H */

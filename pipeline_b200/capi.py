@@ -1,0 +1,506 @@
+"""ctypes binding of include/dpcu.h (pipeline_b200/lib/libdpcu.so).
+
+This is plumbing for the Python test-suite and bench.py; the product is the shared library
+and the C++ ``dp::culling::cuda::Manager`` on top of it.  Loading fails loudly when the
+library has not been built - there is no fallback of any kind.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM = 1, 2, 3, 4
+MAX_VIEWS = 8
+
+_vp = C.c_void_p
+_u32p = C.POINTER(C.c_uint32)
+_f32p = C.POINTER(C.c_float)
+_szp = C.POINTER(C.c_size_t)
+
+_lib = None
+
+
+class DpcuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dpcu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C pipeline_b200/csrc); there is no fallback path" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.dpcuGetLastError.restype = C.c_char_p
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DpcuError(rc, lib().dpcuGetLastError().decode(errors="replace"))
+
+
+def _declare(L):
+    sig = {
+        "dpcuDeviceCount": [C.POINTER(C.c_int)],
+        "dpcuDeviceSelect": [C.c_int],
+        "dpcuDeviceCurrent": [C.POINTER(C.c_int)],
+        "dpcuDeviceSynchronize": [],
+        "dpcuDeviceInfo": [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), _szp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "dpcuDeviceEnablePeerAccess": [C.c_int, C.c_int],
+        "dpcuBufferCreate": [C.POINTER(_vp), C.c_size_t],
+        "dpcuBufferDestroy": [_vp],
+        "dpcuBufferSize": [_vp, _szp],
+        "dpcuBufferDevicePointer": [_vp, C.POINTER(_vp)],
+        "dpcuBufferUpload": [_vp, C.c_size_t, _vp, C.c_size_t, _vp],
+        "dpcuBufferDownload": [_vp, C.c_size_t, _vp, C.c_size_t, _vp],
+        "dpcuBufferFill": [_vp, C.c_int, C.c_size_t, C.c_size_t],
+        "dpcuHostBufferCreate": [C.POINTER(_vp), C.c_size_t, C.c_uint],
+        "dpcuHostBufferDestroy": [_vp],
+        "dpcuHostBufferPointer": [_vp, C.POINTER(_vp)],
+        "dpcuHostBufferSize": [_vp, _szp],
+        "dpcuStreamCreate": [C.POINTER(_vp), C.c_int, C.c_int],
+        "dpcuStreamDestroy": [_vp],
+        "dpcuStreamSynchronize": [_vp],
+        "dpcuStreamIsCompleted": [_vp, C.POINTER(C.c_int)],
+        "dpcuStreamWaitEvent": [_vp, _vp],
+        "dpcuStreamNative": [_vp, C.POINTER(_vp)],
+        "dpcuEventCreate": [C.POINTER(_vp), C.c_uint],
+        "dpcuEventDestroy": [_vp],
+        "dpcuEventRecord": [_vp, _vp],
+        "dpcuEventSynchronize": [_vp],
+        "dpcuEventIsCompleted": [_vp, C.POINTER(C.c_int)],
+        "dpcuEventElapsedMs": [_vp, _vp, C.POINTER(C.c_float)],
+        "dpcuCullCreate": [C.POINTER(_vp), C.c_int],
+        "dpcuCullDestroy": [_vp],
+        "dpcuCullSetObjects": [_vp, _vp, _vp, _vp, C.c_size_t, C.c_int],
+        "dpcuCullSetObjectRange": [_vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.c_int],
+        "dpcuCullGetObjectCount": [_vp, _szp],
+        "dpcuCullSetMatrices": [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int],
+        "dpcuCullUpdateMatrices": [_vp, _u32p, C.c_size_t, _vp, C.c_size_t, C.c_int],
+        "dpcuCullBindMatrices": [_vp, _vp, C.c_size_t],
+        "dpcuCullGetMatrixCount": [_vp, _szp],
+        "dpcuCullResultCreate": [_vp, C.POINTER(_vp)],
+        "dpcuCullResultDestroy": [_vp],
+        "dpcuCullRun": [_vp, C.POINTER(_vp), _f32p, C.c_int, _vp],
+        "dpcuCullResultGetBits": [_vp, _u32p, C.c_size_t],
+        "dpcuCullResultGetChangedCount": [_vp, _szp],
+        "dpcuCullResultGetChanged": [_vp, _u32p, C.c_size_t, _szp],
+        "dpcuCullResultIsVisible": [_vp, C.c_size_t, C.POINTER(C.c_int)],
+        "dpcuCullResultMoveBit": [_vp, C.c_size_t, C.c_size_t],
+        "dpcuCullResultDevicePointers": [_vp, C.POINTER(_vp), _szp, C.POINTER(_vp), C.POINTER(_vp)],
+        "dpcuCullGetBoundingBox": [_vp, _f32p],
+        "dpcuCullSetOption": [_vp, C.c_int, C.c_int],
+        "dpcuCullGetOption": [_vp, C.c_int, C.POINTER(C.c_int)],
+        "dpcuCullGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
+        "dpcuCullResultSetPeerBits": [_vp, C.POINTER(_vp), C.c_int, C.c_size_t],
+        "dpcuIpcGetHandle": [_vp, C.c_char_p],
+        "dpcuIpcOpen": [C.c_char_p, C.POINTER(_vp)],
+        "dpcuIpcClose": [_vp],
+        "dpcuTreeCreate": [C.POINTER(_vp), C.c_int],
+        "dpcuTreeDestroy": [_vp],
+        "dpcuTreeSetTopology": [_vp, _u32p, _u32p, C.c_int, C.c_size_t],
+        "dpcuTreeSetLocals": [_vp, C.c_size_t, C.c_size_t, _vp, C.c_int],
+        "dpcuTreeUpdateLocals": [_vp, _u32p, C.c_size_t, _vp, C.c_int],
+        "dpcuTreeMarkDirty": [_vp, C.c_size_t, C.c_size_t],
+        "dpcuTreeCompute": [_vp, _vp],
+        "dpcuTreeWorldDevicePointer": [_vp, C.POINTER(_vp), _szp],
+        "dpcuTreeLocalDevicePointer": [_vp, C.POINTER(_vp), _szp],
+        "dpcuTreeGetWorld": [_vp, C.c_size_t, C.c_size_t, _vp],
+        "dpcuTreeGetDirtyWorld": [_vp, _u32p, C.c_size_t],
+        "dpcuTreeGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
+        "dpcuSceneGenerate": [C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32, _vp, _vp, _vp, _vp],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = C.c_int
+    L.dpcuGetVersion.restype = C.c_int
+
+
+EXPORTED = None  # filled by tests from include/dpcu.h
+
+
+def _ptr(a):
+    """numpy array -> void*, int -> void* (device pointer), None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+# ------------------------------------------------------------------------------ dp/cuda layer
+def device_count():
+    n = C.c_int(0)
+    check(lib().dpcuDeviceCount(C.byref(n)))
+    return n.value
+
+
+def device_select(i):
+    check(lib().dpcuDeviceSelect(i))
+
+
+def device_sync():
+    check(lib().dpcuDeviceSynchronize())
+
+
+def device_info(i=0):
+    name = C.create_string_buffer(256)
+    sm, mem, maj, mnr = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+    check(lib().dpcuDeviceInfo(i, name, 256, C.byref(sm), C.byref(mem), C.byref(maj), C.byref(mnr)))
+    return {"name": name.value.decode(), "sms": sm.value, "mem": mem.value, "cc": (maj.value, mnr.value)}
+
+
+class Buffer:
+    """dp::cuda::Buffer"""
+
+    def __init__(self, nbytes):
+        self.h = _vp()
+        check(lib().dpcuBufferCreate(C.byref(self.h), nbytes))
+        self.nbytes = nbytes
+
+    @property
+    def ptr(self):
+        p = _vp()
+        check(lib().dpcuBufferDevicePointer(self.h, C.byref(p)))
+        return p.value or 0
+
+    def upload(self, arr, offset=0, stream=None):
+        check(lib().dpcuBufferUpload(self.h, offset, _ptr(arr), arr.nbytes, stream.h if stream else None))
+
+    def download(self, arr, offset=0, stream=None):
+        check(lib().dpcuBufferDownload(self.h, offset, _ptr(arr), arr.nbytes, stream.h if stream else None))
+        return arr
+
+    def fill(self, byte, nbytes=None, offset=0):
+        check(lib().dpcuBufferFill(self.h, byte, self.nbytes if nbytes is None else nbytes, offset))
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuBufferDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostBuffer:
+    """dp::cuda::BufferHost (pinned)."""
+
+    def __init__(self, nbytes, flags=0):
+        self.h = _vp()
+        check(lib().dpcuHostBufferCreate(C.byref(self.h), nbytes, flags))
+        self.nbytes = nbytes
+        p = _vp()
+        check(lib().dpcuHostBufferPointer(self.h, C.byref(p)))
+        self.ptr = p.value or 0
+
+    def array(self, dtype, count=None, offset=0):
+        dtype = np.dtype(dtype)
+        if count is None:
+            count = (self.nbytes - offset) // dtype.itemsize
+        buf = (C.c_char * (count * dtype.itemsize)).from_address(self.ptr + offset)
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuHostBufferDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Stream:
+    def __init__(self, blocking=False, priority=0):
+        self.h = _vp()
+        check(lib().dpcuStreamCreate(C.byref(self.h), int(blocking), priority))
+
+    def sync(self):
+        check(lib().dpcuStreamSynchronize(self.h))
+
+    def completed(self):
+        c = C.c_int()
+        check(lib().dpcuStreamIsCompleted(self.h, C.byref(c)))
+        return bool(c.value)
+
+    def wait(self, event):
+        check(lib().dpcuStreamWaitEvent(self.h, event.h))
+
+    @property
+    def native(self):
+        p = _vp()
+        check(lib().dpcuStreamNative(self.h, C.byref(p)))
+        return p.value or 0
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuStreamDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Event:
+    def __init__(self, flags=0):
+        self.h = _vp()
+        check(lib().dpcuEventCreate(C.byref(self.h), flags))
+
+    def record(self, stream=None):
+        check(lib().dpcuEventRecord(self.h, stream.h if stream else None))
+
+    def sync(self):
+        check(lib().dpcuEventSynchronize(self.h))
+
+    def elapsed_ms(self, stop):
+        ms = C.c_float()
+        check(lib().dpcuEventElapsedMs(self.h, stop.h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuEventDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------ culling layer
+class CullResult:
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = _vp()
+        check(lib().dpcuCullResultCreate(ctx.h, C.byref(self.h)))
+
+    def bits(self):
+        n = self.ctx.count()
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        check(lib().dpcuCullResultGetBits(self.h, words.ctypes.data_as(_u32p), len(words)))
+        return words
+
+    def changed_count(self):
+        c = C.c_size_t()
+        check(lib().dpcuCullResultGetChangedCount(self.h, C.byref(c)))
+        return c.value
+
+    def changed(self):
+        n = self.changed_count()
+        out = np.empty(max(n, 1), dtype=np.uint32)
+        c = C.c_size_t()
+        check(lib().dpcuCullResultGetChanged(self.h, out.ctypes.data_as(_u32p), n, C.byref(c)))
+        return out[:n].copy()
+
+    def is_visible(self, index):
+        v = C.c_int()
+        check(lib().dpcuCullResultIsVisible(self.h, index, C.byref(v)))
+        return bool(v.value)
+
+    def move_bit(self, old, new):
+        check(lib().dpcuCullResultMoveBit(self.h, old, new))
+
+    def device_pointers(self):
+        bits, chg, cnt, nw = _vp(), _vp(), _vp(), C.c_size_t()
+        check(lib().dpcuCullResultDevicePointers(self.h, C.byref(bits), C.byref(nw), C.byref(chg), C.byref(cnt)))
+        return {"bits": bits.value or 0, "n_words": nw.value, "changed": chg.value or 0, "count": cnt.value or 0}
+
+    def set_peer_bits(self, pointers, word_offset):
+        arr = (_vp * max(len(pointers), 1))(*[(_vp(p) if p else None) for p in pointers])
+        check(lib().dpcuCullResultSetPeerBits(self.h, arr, len(pointers), word_offset))
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuCullResultDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Cull:
+    """One culling group on one device (dpcuCull)."""
+
+    def __init__(self, device=0):
+        self.h = _vp()
+        check(lib().dpcuCullCreate(C.byref(self.h), device))
+        self.device = device
+        self._mat_src = None
+
+    def set_objects(self, lower4, extent4, tidx, memspace=MEM_HOST, n=None):
+        if n is None:
+            n = len(lower4)
+        check(lib().dpcuCullSetObjects(self.h, _ptr(lower4), _ptr(extent4), _ptr(tidx), n, memspace))
+
+    def set_object_range(self, first, lower4, extent4, tidx, memspace=MEM_HOST, count=None):
+        if count is None:
+            count = len(lower4)
+        check(lib().dpcuCullSetObjectRange(self.h, first, count, _ptr(lower4), _ptr(extent4), _ptr(tidx), memspace))
+
+    def count(self):
+        c = C.c_size_t()
+        check(lib().dpcuCullGetObjectCount(self.h, C.byref(c)))
+        return c.value
+
+    def set_matrices(self, mats, stride=64, count=None, memspace=MEM_HOST):
+        if count is None:
+            count = mats.nbytes // stride
+        check(lib().dpcuCullSetMatrices(self.h, _ptr(mats), count, stride, memspace))
+        if memspace == MEM_HOST:
+            self._mat_src = (mats, stride)
+
+    def update_matrices(self, indices, mats, stride=64):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        check(lib().dpcuCullUpdateMatrices(self.h, idx.ctypes.data_as(_u32p), len(idx), _ptr(mats), stride, MEM_HOST))
+
+    def update_matrices_from_source(self, indices):
+        mats, stride = self._mat_src
+        self.update_matrices(indices, mats, stride)
+
+    def bind_matrices(self, device_ptr, count):
+        check(lib().dpcuCullBindMatrices(self.h, device_ptr, count))
+
+    def matrix_count(self):
+        c = C.c_size_t()
+        check(lib().dpcuCullGetMatrixCount(self.h, C.byref(c)))
+        return c.value
+
+    def result_create(self):
+        return CullResult(self)
+
+    def run(self, results, vps, stream=None):
+        vps = np.ascontiguousarray(vps, dtype=np.float32).reshape(-1)
+        nv = len(results)
+        assert len(vps) == 16 * nv
+        arr = (_vp * nv)(*[r.h for r in results])
+        check(lib().dpcuCullRun(self.h, arr, vps.ctypes.data_as(_f32p), nv, stream.h if stream else None))
+
+    def bounding_box(self):
+        out = np.zeros(6, dtype=np.float32)
+        check(lib().dpcuCullGetBoundingBox(self.h, out.ctypes.data_as(_f32p)))
+        return out
+
+    def set_option(self, opt, value):
+        check(lib().dpcuCullSetOption(self.h, opt, value))
+
+    def get_option(self, opt):
+        v = C.c_int()
+        check(lib().dpcuCullGetOption(self.h, opt, C.byref(v)))
+        return v.value
+
+    def launches(self):
+        v = C.c_uint64()
+        check(lib().dpcuCullGetLaunchCount(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuCullDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------ transform layer
+class Tree:
+    def __init__(self, device=0):
+        self.h = _vp()
+        check(lib().dpcuTreeCreate(C.byref(self.h), device))
+        self.n_nodes = 0
+
+    def set_topology(self, entries, level_offsets, n_nodes):
+        entries = np.ascontiguousarray(entries, np.uint32).reshape(-1)
+        level_offsets = np.ascontiguousarray(level_offsets, np.uint32)
+        check(lib().dpcuTreeSetTopology(self.h, entries.ctypes.data_as(_u32p), level_offsets.ctypes.data_as(_u32p),
+                                        len(level_offsets) - 1, n_nodes))
+        self.n_nodes = n_nodes
+
+    def set_locals(self, first, mats, memspace=MEM_HOST, count=None):
+        if count is None:
+            count = mats.nbytes // 64
+        check(lib().dpcuTreeSetLocals(self.h, first, count, _ptr(mats), memspace))
+
+    def update_locals(self, indices, mats):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        mats = np.ascontiguousarray(mats, np.float32)
+        check(lib().dpcuTreeUpdateLocals(self.h, idx.ctypes.data_as(_u32p), len(idx), _ptr(mats), MEM_HOST))
+
+    def mark_dirty(self, first, count):
+        check(lib().dpcuTreeMarkDirty(self.h, first, count))
+
+    def compute(self, stream=None):
+        check(lib().dpcuTreeCompute(self.h, stream.h if stream else None))
+
+    def world_ptr(self):
+        p, n = _vp(), C.c_size_t()
+        check(lib().dpcuTreeWorldDevicePointer(self.h, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def local_ptr(self):
+        p, n = _vp(), C.c_size_t()
+        check(lib().dpcuTreeLocalDevicePointer(self.h, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def world(self, first=0, count=None):
+        if count is None:
+            count = self.n_nodes - first
+        out = np.zeros((count, 4, 4), dtype=np.float32)
+        check(lib().dpcuTreeGetWorld(self.h, first, count, _ptr(out)))
+        return out
+
+    def dirty_world(self):
+        words = np.zeros((self.n_nodes + 31) // 32, dtype=np.uint32)
+        check(lib().dpcuTreeGetDirtyWorld(self.h, words.ctypes.data_as(_u32p), len(words)))
+        return words
+
+    def launches(self):
+        v = C.c_uint64()
+        check(lib().dpcuTreeGetLaunchCount(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            check(lib().dpcuTreeDestroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scene_generate(seed, first, count, index_base, lower_ptr, extent_ptr, mats_ptr, stream=None):
+    check(lib().dpcuSceneGenerate(seed, first, count, index_base, lower_ptr, extent_ptr, mats_ptr,
+                                  stream.h if stream else None))

@@ -1,0 +1,974 @@
+// Culling layer of the C ABI: device mirror of a culling group and of its results, the
+// frustum-cull kernels (K2), the ordered changed-list compaction and the group bounding box (K4).
+//
+// Replaces, on the GPU, the reference's hot loops B, C and D:
+//   GroupCPU::updateOBBs          dp/culling/cpu/src/ManagerImpl.cpp:114-162
+//   isVisible + visible.setBit    dp/culling/cpu/src/ManagerImpl.cpp:263-289,511-514
+//   ResultBitSet::updateChanged   dp/culling/src/ResultBitSet.cpp:61-108
+//
+// HBM layout (all arrays 256-byte aligned cudaMalloc blocks):
+//   lowerIdx[n]  float4  (box.lower.xyz, transformIndex as raw u32 bits)          16 B / object
+//   extent[n]    float4  (box.upper - box.lower, 0)                               16 B / object
+//   mats[m]      4 x float4 per matrix, row-major, 64-byte stride                 64 B / matrix
+//   per result:  bits[ceil(n/32)] u32 (previous visibility, updated in place),
+//                chg[ceil(n/32)]  u32 (bits that flipped in the last cull),
+//                changed[n] u32 (ascending group indices), seg[]/super[] u32 changed-counts
+//                per 8192 / 1 Mi objects, count u32.
+//
+// One cull = memset(counters) -> cull kernel (one pass over the objects for up to 8 views:
+// ballot -> word, XOR with the previous word, popc into the segment counters) -> compaction
+// kernel (segment-ordered expansion of the flipped bits into the changed list).
+//
+// This translation unit is compiled with -fmad=false (exact mode).  dpcu_cull_fma.cu includes
+// it again with DPCU_FMA_VARIANT defined and -fmad=true to provide the reporting-only fast mode.
+#include "cull_math.cuh"
+#include "dpcu_internal.h"
+
+#include <new>
+
+namespace dpcu
+{
+  constexpr int      kCullThreads    = 256;                 // objects per tile = threads per CTA
+  constexpr int      kWordsPerTile   = kCullThreads / 32;
+  constexpr uint32_t kSegObjectsLog2 = 13;                  // 8192 objects = 256 words per segment
+  constexpr uint32_t kSegWords       = 1u << ( kSegObjectsLog2 - 5 );
+  constexpr uint32_t kSuperSegsLog2  = 7;                   // 128 segments = 1 Mi objects per super-segment
+  constexpr int      kMaxPeers       = 8;
+
+  struct ViewOut
+  {
+    uint32_t *bits;      // in: previous visibility, out: new visibility
+    uint32_t *chg;       // out: bits that flipped
+    uint32_t *seg;       // += popc per 8192-object segment
+    uint32_t *super;     // += popc per 1 Mi-object super-segment
+    uint32_t *peer[kMaxPeers];   // optional: full bitsets on peer GPUs (NVLink stores)
+  };
+
+  template <int NV>
+  struct CullArgs
+  {
+    float4 const *lowerIdx;
+    float4 const *extent;
+    float4 const *mats;
+    uint32_t      n;
+    uint32_t      nTiles;
+    uint32_t      nPeers;
+    uint32_t      peerWordOffset;
+    int           buildChanged;
+    ViewOut       out[NV];
+    float4        vp[NV][4];
+  };
+
+#ifndef DPCU_FMA_VARIANT
+#define DPCU_KERNEL_NAME( name ) name
+#else
+#define DPCU_KERNEL_NAME( name ) name##_fma
+#endif
+
+  // ------------------------------------------------------------------------------------------
+  // K2, direct variant: one thread per object, six 16-byte loads, persistent grid-stride tiles.
+  template <int NV>
+  __global__ void __launch_bounds__( kCullThreads )
+  DPCU_KERNEL_NAME( cullDirectKernel )( const __grid_constant__ CullArgs<NV> a )
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    for ( uint32_t tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x )
+    {
+      const uint32_t i    = tile * kCullThreads + threadIdx.x;
+      const bool     live = i < a.n;
+      const uint32_t word = i >> 5;
+
+      // previous visibility words are fetched early by the lane that will need them
+      uint32_t oldBits[NV];
+      if ( lane == 0 && live )
+      {
+#pragma unroll
+        for ( int v = 0; v < NV; ++v ) oldBits[v] = a.out[v].bits[word];
+      }
+
+      bool vis[NV];
+#pragma unroll
+      for ( int v = 0; v < NV; ++v ) vis[v] = false;
+
+      if ( live )
+      {
+        const float4 lo = ldStream( a.lowerIdx + i );
+        const float4 ex = ldStream( a.extent + i );
+        float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
+        const float4 m0 = __ldg( m + 0 );
+        const float4 m1 = __ldg( m + 1 );
+        const float4 m2 = __ldg( m + 2 );
+        const float4 m3 = __ldg( m + 3 );
+        const Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+#pragma unroll
+        for ( int v = 0; v < NV; ++v )
+        {
+          vis[v] = obbVisible( obb, a.vp[v][0], a.vp[v][1], a.vp[v][2], a.vp[v][3] );
+        }
+      }
+
+#pragma unroll
+      for ( int v = 0; v < NV; ++v )
+      {
+        const uint32_t nw = __ballot_sync( 0xffffffffu, vis[v] );
+        if ( lane == 0 && live )
+        {
+          ViewOut const &o = a.out[v];
+          o.bits[word] = nw;
+          for ( uint32_t p = 0; p < a.nPeers; ++p )
+          {
+            if ( o.peer[p] ) o.peer[p][a.peerWordOffset + word] = nw;
+          }
+          if ( a.buildChanged )
+          {
+            const uint32_t c = oldBits[v] ^ nw;
+            o.chg[word] = c;
+            if ( c )
+            {
+              const uint32_t pc = __popc( c );
+              atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), pc );
+              atomicAdd( o.super + ( word >> ( kSegObjectsLog2 - 5 + kSuperSegsLog2 ) ), pc );
+            }
+          }
+        }
+      }
+    }
+  }
+
+#ifndef DPCU_FMA_VARIANT
+  // ------------------------------------------------------------------------------------------
+  // Ordered changed list.  One CTA per 8192-object segment and view: the CTA's base offset is
+  // the sum of the counters of all earlier segments (two levels, so at most 255 + 127 reads),
+  // then a block scan over the popcounts of its 256 flipped-bit words places every index.
+  struct CompactArgs
+  {
+    uint32_t const *chg[DPCU_MAX_VIEWS];
+    uint32_t const *seg[DPCU_MAX_VIEWS];
+    uint32_t const *super[DPCU_MAX_VIEWS];
+    uint32_t       *changed[DPCU_MAX_VIEWS];
+    uint32_t       *count[DPCU_MAX_VIEWS];
+    uint32_t        nWords;
+    uint32_t        nSegs;
+  };
+
+  __global__ void __launch_bounds__( 256 ) compactChangedKernel( const __grid_constant__ CompactArgs a )
+  {
+    const uint32_t v    = blockIdx.y;
+    const uint32_t s    = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool     last = ( s == a.nSegs - 1 );
+    const uint32_t mine = a.seg[v][s];
+    if ( mine == 0 && !last ) return;
+
+    __shared__ uint32_t sBase;
+    __shared__ uint32_t sWarp[8];
+
+    if ( warp == 0 )
+    {
+      uint32_t sum = 0;
+      const uint32_t sup = s >> kSuperSegsLog2;
+      for ( uint32_t k = lane; k < sup; k += 32 ) sum += a.super[v][k];
+      for ( uint32_t k = ( sup << kSuperSegsLog2 ) + lane; k < s; k += 32 ) sum += a.seg[v][k];
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 ) sum += __shfl_xor_sync( 0xffffffffu, sum, d );
+      if ( lane == 0 )
+      {
+        sBase = sum;
+        if ( last ) *a.count[v] = sum + mine;
+      }
+    }
+
+    const uint32_t w = s * kSegWords + threadIdx.x;
+    uint32_t c = ( mine && w < a.nWords ) ? a.chg[v][w] : 0u;
+    const uint32_t pc = __popc( c );
+    uint32_t incl = pc;
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 )
+    {
+      uint32_t t = __shfl_up_sync( 0xffffffffu, incl, d );
+      if ( lane >= d ) incl += t;
+    }
+    if ( lane == 31 ) sWarp[warp] = incl;
+    __syncthreads();
+    if ( mine == 0 ) return;
+    uint32_t off = sBase + incl - pc;
+    for ( uint32_t k = 0; k < warp; ++k ) off += sWarp[k];
+    uint32_t *out = a.changed[v];
+    const uint32_t base = w << 5;
+    while ( c )
+    {
+      const uint32_t b = __ffs( c ) - 1;
+      out[off++] = base + b;
+      c &= c - 1;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // object upload: pack transformIndex into lower.w, zero extent.w, track the largest index
+  __global__ void packObjectsKernel( float4 const *lower, float4 const *extent, uint32_t const *tidx, uint32_t n,
+                                     float4 *lowerIdx, float4 *extentOut, uint32_t *maxIndex )
+  {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;
+    if ( i < n )
+    {
+      float4 lo = lower[i];
+      float4 ex = extent[i];
+      uint32_t t = tidx ? tidx[i] : __float_as_uint( lo.w );
+      lo.w = __uint_as_float( t );
+      ex.w = 0.0f;
+      lowerIdx[i]  = lo;
+      extentOut[i] = ex;
+      m = t;
+    }
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 ) m = max( m, __shfl_xor_sync( 0xffffffffu, m, d ) );
+    if ( ( threadIdx.x & 31 ) == 0 && m ) atomicMax( maxIndex, m );
+  }
+
+  // matrices[indices[k]] = packed[k]
+  __global__ void scatterMatricesKernel( uint32_t const *indices, float4 const *packed, uint32_t n, float4 *mats )
+  {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per matrix row
+    if ( t < n * 4u ) mats[4ull * indices[t >> 2] + ( t & 3u )] = packed[t];
+  }
+
+  // strided device -> packed device copy (device-side groupSetMatrices with stride != 64)
+  __global__ void gatherStridedKernel( char const *src, size_t stride, uint32_t count, float *dst )
+  {
+    size_t t = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;   // one thread per float
+    if ( t < size_t( count ) * 16 ) dst[t] = *reinterpret_cast<float const *>( src + ( t >> 4 ) * stride + ( t & 15 ) * 4 );
+  }
+
+  // ResultBitSet incarnation step (dp/culling/src/ResultBitSet.cpp:65-79): bits of objects
+  // [oldN, newN) become 1, bits >= newN become 0, older bits are kept.
+  __global__ void resizeBitsKernel( uint32_t *bits, uint32_t oldN, uint32_t newN, uint32_t capWords )
+  {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( w >= capWords ) return;
+    const uint64_t lo = uint64_t( w ) << 5, hi = lo + 32;
+    if ( hi <= oldN && hi <= newN ) return;
+    uint32_t x = bits[w];
+    uint32_t keep  = ( lo >= oldN ) ? 0u : ( hi <= oldN ? ~0u : ( ~0u >> ( 32 - ( oldN - lo ) ) ) );   // bits < oldN
+    uint32_t valid = ( lo >= newN ) ? 0u : ( hi <= newN ? ~0u : ( ~0u >> ( 32 - ( newN - lo ) ) ) );   // bits < newN
+    x = ( ( x & keep ) | ~keep ) & valid;
+    bits[w] = x;
+  }
+
+  // ResultBitSet::onNotify (dp/culling/src/ResultBitSet.cpp:110-128)
+  __global__ void moveBitKernel( uint32_t *bits, uint32_t size, uint32_t oldIndex, uint32_t newIndex )
+  {
+    if ( newIndex < size )
+    {
+      uint32_t value = 1u;
+      if ( oldIndex < size ) value = ( bits[oldIndex >> 5] >> ( oldIndex & 31 ) ) & 1u;
+      uint32_t w = bits[newIndex >> 5];
+      w = value ? ( w | ( 1u << ( newIndex & 31 ) ) ) : ( w & ~( 1u << ( newIndex & 31 ) ) );
+      bits[newIndex >> 5] = w;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // K4: group bounding box, ManagerBitSet::calculateBoundingBox scalar branch
+  // (dp/culling/src/ManagerBitSet.cpp:268-306).  min/max are order independent, so a tree
+  // reduction gives the reference's sequential Box4f::update result bit for bit, except that
+  // Boxnt::update skips NaN coordinates (both comparisons false) - fminf/fmaxf do the same.
+  // Signed zeros: update() keeps the first of +0/-0 it met; the final box is compared with ==
+  // semantics by every consumer, and the test-suite compares with np.array_equal (-0 == +0).
+  struct BoxAcc
+  {
+    float lo[3], hi[3];
+  };
+
+  __device__ __forceinline__ void boxUpdate( BoxAcc &b, float4 p )
+  {
+    b.lo[0] = fminf( b.lo[0], p.x ); b.hi[0] = fmaxf( b.hi[0], p.x );
+    b.lo[1] = fminf( b.lo[1], p.y ); b.hi[1] = fmaxf( b.hi[1], p.y );
+    b.lo[2] = fminf( b.lo[2], p.z ); b.hi[2] = fmaxf( b.hi[2], p.z );
+  }
+
+  __device__ __forceinline__ uint32_t orderedKey( float f )
+  {
+    uint32_t u = __float_as_uint( f );
+    return ( u & 0x80000000u ) ? ~u : ( u | 0x80000000u );
+  }
+
+  __global__ void __launch_bounds__( 256 ) boundingBoxKernel( float4 const *lowerIdx, float4 const *extent,
+                                                              float4 const *mats, uint32_t n, uint32_t *keys /* 3 min, 3 max */ )
+  {
+    const float FMAX = 3.402823466e+38f;
+    BoxAcc b = { { FMAX, FMAX, FMAX }, { -FMAX, -FMAX, -FMAX } };
+    for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+    {
+      const float4 lo = ldStream( lowerIdx + i );
+      const float4 ex = ldStream( extent + i );
+      float4 const *m = mats + 4ull * __float_as_uint( lo.w );
+      const Obb o = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, __ldg( m ), __ldg( m + 1 ), __ldg( m + 2 ), __ldg( m + 3 ) );
+      const float4 v0 = o.pt;
+      const float4 v1 = add4( v0, o.ax );
+      const float4 v2 = add4( v0, o.ay );
+      const float4 v3 = add4( v1, o.ay );
+      boxUpdate( b, v0 ); boxUpdate( b, v1 ); boxUpdate( b, v2 ); boxUpdate( b, v3 );
+      boxUpdate( b, add4( v0, o.az ) ); boxUpdate( b, add4( v1, o.az ) );
+      boxUpdate( b, add4( v2, o.az ) ); boxUpdate( b, add4( v3, o.az ) );
+    }
+#pragma unroll
+    for ( int k = 0; k < 3; ++k )
+    {
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 )
+      {
+        b.lo[k] = fminf( b.lo[k], __shfl_xor_sync( 0xffffffffu, b.lo[k], d ) );
+        b.hi[k] = fmaxf( b.hi[k], __shfl_xor_sync( 0xffffffffu, b.hi[k], d ) );
+      }
+    }
+    if ( ( threadIdx.x & 31 ) == 0 )
+    {
+#pragma unroll
+      for ( int k = 0; k < 3; ++k )
+      {
+        atomicMin( keys + k, orderedKey( b.lo[k] ) );
+        atomicMax( keys + 3 + k, orderedKey( b.hi[k] ) );
+      }
+    }
+  }
+#endif   // !DPCU_FMA_VARIANT
+}   // namespace dpcu
+
+#ifdef DPCU_FMA_VARIANT
+// launcher used by the exact translation unit for DPCU_CULL_OPT_FMA = 1
+namespace dpcu
+{
+  template <int NV>
+  cudaError_t launchCullDirectFma( CullArgs<NV> const &args, int grid, cudaStream_t stream )
+  {
+    cullDirectKernel_fma<NV><<<grid, kCullThreads, 0, stream>>>( args );
+    return cudaGetLastError();
+  }
+  template <int NV> int occupancyCullDirectFma()
+  {
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, cullDirectKernel_fma<NV>, kCullThreads, 0 );
+    return b;
+  }
+#define DPCU_INSTANTIATE( NV )                                                                        \
+  template cudaError_t launchCullDirectFma<NV>( CullArgs<NV> const &, int, cudaStream_t );            \
+  template int occupancyCullDirectFma<NV>();
+  DPCU_INSTANTIATE( 1 ) DPCU_INSTANTIATE( 2 ) DPCU_INSTANTIATE( 3 ) DPCU_INSTANTIATE( 4 )
+  DPCU_INSTANTIATE( 5 ) DPCU_INSTANTIATE( 6 ) DPCU_INSTANTIATE( 7 ) DPCU_INSTANTIATE( 8 )
+}
+#else
+
+namespace dpcu
+{
+  template <int NV> cudaError_t launchCullDirectFma( CullArgs<NV> const &args, int grid, cudaStream_t stream );
+  template <int NV> int occupancyCullDirectFma();
+}
+
+// =============================================================================================
+// host side
+struct dpcuCullResult
+{
+  dpcuCull *ctx = nullptr;
+  dpcu::DeviceArray bits, chg, changed, counters;   // counters: seg[] | super[] | count
+  size_t   n = 0;                // object count the stored bits are valid for (ResultBitSet::m_results size)
+  size_t   capWords = 0;
+  size_t   nSegsCap = 0;
+  bool     ran = false;          // a changed list exists
+  cudaStream_t lastStream = nullptr;
+  uint32_t *peer[dpcu::kMaxPeers] = { nullptr };
+  int      nPeers = 0;
+  size_t   peerWordOffset = 0;
+  dpcuCullResult *next = nullptr, *prev = nullptr;
+
+  uint32_t *segPtr() const { return static_cast<uint32_t *>( counters.ptr ); }
+  uint32_t *superPtr() const { return segPtr() + nSegsCap; }
+  uint32_t *countPtr() const { return superPtr() + ( nSegsCap >> dpcu::kSuperSegsLog2 ) + 1; }
+};
+
+struct dpcuCull
+{
+  int          device = 0;
+  int          smCount = 0;
+  cudaStream_t stream = nullptr;
+  dpcu::DeviceArray lowerIdx, extent, mats, scratch, maxIndex;
+  dpcu::PinnedArray staging;
+  float const *boundMats = nullptr;      // borrowed device matrices (dpcuCullBindMatrices)
+  size_t       n = 0, nMats = 0;
+  uint32_t     maxTransformIndex = 0;
+  bool         maxIndexKnown = true;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0;
+  uint64_t     launches = 0;
+  dpcuCullResult *results = nullptr;
+
+  float4 const *matsPtr() const { return boundMats ? reinterpret_cast<float4 const *>( boundMats ) : static_cast<float4 const *>( mats.ptr ); }
+};
+
+namespace dpcu
+{
+  static int uploadOrCopy( void *dst, void const *src, size_t bytes, int memspace, dpcuCull *ctx )
+  {
+    if ( !bytes ) return DPCU_OK;
+    if ( memspace == DPCU_MEM_DEVICE )
+    {
+      DPCU_CUDA( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream ) );
+    }
+    else
+    {
+      // pageable or pinned caller memory: the copy is complete (w.r.t. the host buffer) on return
+      DPCU_CUDA( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+      DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    }
+    return DPCU_OK;
+  }
+
+  static int refreshMaxIndex( dpcuCull *ctx )
+  {
+    if ( !ctx->maxIndexKnown )
+    {
+      DPCU_CUDA( cudaMemcpyAsync( &ctx->maxTransformIndex, ctx->maxIndex.ptr, sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx->stream ) );
+      DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
+      ctx->maxIndexKnown = true;
+    }
+    return DPCU_OK;
+  }
+
+  static int ensureResultCapacity( dpcuCullResult *r, size_t n, cudaStream_t stream )
+  {
+    dpcuCull *ctx = r->ctx;
+    // words padded to whole segments so the compaction kernel can read full 256-word rows
+    size_t nSegs = divUp( n, size_t( 1 ) << kSegObjectsLog2 );
+    size_t words = ( nSegs ? nSegs : 1 ) * kSegWords;
+    if ( words > r->capWords )
+    {
+      size_t oldBytes = r->capWords * 4;
+      DPCU_TRY( r->bits.reserve( words * 4, true, stream ) );
+      size_t newCapWords = r->bits.capacity / 4;
+      DPCU_CUDA( cudaMemsetAsync( static_cast<char *>( r->bits.ptr ) + oldBytes, 0, r->bits.capacity - oldBytes, stream ) );
+      DPCU_TRY( r->chg.reserve( newCapWords * 4, false, stream ) );
+      DPCU_CUDA( cudaMemsetAsync( r->chg.ptr, 0, r->chg.capacity, stream ) );
+      r->capWords = newCapWords;
+      if ( r->nPeers == 0 ) { /* local only */ }
+    }
+    if ( ctx->optChanged ) DPCU_TRY( r->changed.reserve( ( n ? n : 1 ) * 4, false, stream ) );
+    if ( nSegs + 1 > r->nSegsCap )
+    {
+      size_t cap = nSegs + 1 + nSegs / 2;
+      cap = ( cap + 127 ) & ~size_t( 127 );
+      size_t entries = cap + ( cap >> kSuperSegsLog2 ) + 1 + 1;
+      DPCU_TRY( r->counters.reserve( entries * 4, false, stream ) );
+      r->nSegsCap = cap;
+      DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, r->counters.capacity, stream ) );
+    }
+    return DPCU_OK;
+  }
+
+  template <int NV>
+  static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream )
+  {
+    CullArgs<NV> args;
+    memset( &args, 0, sizeof args );
+    args.lowerIdx = static_cast<float4 const *>( ctx->lowerIdx.ptr );
+    args.extent   = static_cast<float4 const *>( ctx->extent.ptr );
+    args.mats     = ctx->matsPtr();
+    args.n        = uint32_t( ctx->n );
+    args.nTiles   = uint32_t( divUp( ctx->n, size_t( kCullThreads ) ) );
+    args.buildChanged = ctx->optChanged;
+    args.nPeers   = 0;
+    for ( int v = 0; v < NV; ++v )
+    {
+      dpcuCullResult *r = results[v];
+      args.out[v].bits  = static_cast<uint32_t *>( r->bits.ptr );
+      args.out[v].chg   = static_cast<uint32_t *>( r->chg.ptr );
+      args.out[v].seg   = r->segPtr();
+      args.out[v].super = r->superPtr();
+      for ( int p = 0; p < kMaxPeers; ++p ) args.out[v].peer[p] = p < r->nPeers ? r->peer[p] : nullptr;
+      if ( uint32_t( r->nPeers ) > args.nPeers ) args.nPeers = uint32_t( r->nPeers );
+      args.peerWordOffset = uint32_t( r->peerWordOffset );
+      memcpy( args.vp[v], vps + 16 * v, 64 );
+    }
+    int perSm = ctx->optCtasPerSm;
+    if ( perSm <= 0 )
+    {
+      if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullDirectKernel<NV>, kCullThreads, 0 );
+      if ( perSm <= 0 ) perSm = 1;
+    }
+    int grid = ctx->smCount * perSm;
+    if ( uint32_t( grid ) > args.nTiles ) grid = int( args.nTiles );
+    if ( ctx->optFma )
+    {
+      DPCU_CUDA( launchCullDirectFma<NV>( args, grid, stream ) );
+    }
+    else
+    {
+      cullDirectKernel<NV><<<grid, kCullThreads, 0, stream>>>( args );
+      DPCU_CUDA( cudaGetLastError() );
+    }
+    ++ctx->launches;
+    return DPCU_OK;
+  }
+}
+
+extern "C"
+{
+  int dpcuCullCreate( dpcuCull **out, int device )
+  {
+    DPCU_REQUIRE( out, "out is NULL" );
+    *out = nullptr;
+    DPCU_TRY( dpcu::requireDevice() );
+    int count = 0;
+    DPCU_CUDA( cudaGetDeviceCount( &count ) );
+    DPCU_REQUIRE( device >= 0 && device < count, "device index out of range" );
+    dpcu::DeviceGuard guard( device );
+    dpcuCull *ctx = new ( std::nothrow ) dpcuCull;
+    if ( !ctx ) return dpcu::fail( DPCU_ERR_OUT_OF_MEMORY, "dpcuCullCreate: host allocation failed" );
+    ctx->device = device;
+    cudaError_t e = cudaDeviceGetAttribute( &ctx->smCount, cudaDevAttrMultiProcessorCount, device );
+    if ( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking );
+    if ( e != cudaSuccess ) { delete ctx; return dpcu::failCuda( e, "dpcuCullCreate", __FILE__, __LINE__ ); }
+    int rc = ctx->maxIndex.reserve( 256, false, ctx->stream );
+    if ( rc != DPCU_OK ) { cudaStreamDestroy( ctx->stream ); delete ctx; return rc; }
+    *out = ctx;
+    return DPCU_OK;
+  }
+
+  int dpcuCullDestroy( dpcuCull *ctx )
+  {
+    if ( !ctx ) return DPCU_OK;
+    if ( ctx->results )
+      return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullDestroy: results of this context are still alive "
+                                                 "(destroy results first; ResultBitSet detaches from its group, ResultBitSet.cpp:51-54)" );
+    dpcu::DeviceGuard guard( ctx->device );
+    cudaStreamSynchronize( ctx->stream );
+    ctx->lowerIdx.release(); ctx->extent.release(); ctx->mats.release(); ctx->scratch.release(); ctx->maxIndex.release();
+    ctx->staging.release();
+    cudaStreamDestroy( ctx->stream );
+    delete ctx;
+    return DPCU_OK;
+  }
+
+  int dpcuCullSetObjectRange( dpcuCull *ctx, size_t first, size_t count, const float *lower4, const float *extent4,
+                              const uint32_t *transformIndex, int memspace )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( first + count <= ctx->n, "range exceeds object count" );
+    DPCU_REQUIRE( !count || ( lower4 && extent4 ), "NULL object arrays" );
+    DPCU_REQUIRE( memspace == DPCU_MEM_DEVICE || transformIndex || !count, "transformIndex may only be NULL for device memory" );
+    if ( !count ) return DPCU_OK;
+    dpcu::DeviceGuard guard( ctx->device );
+    float4 const *lo = nullptr, *ex = nullptr;
+    uint32_t const *ti = nullptr;
+    if ( memspace == DPCU_MEM_HOST )
+    {
+      // stage through scratch: [lower | extent | tidx]
+      size_t bytes = count * ( 16 + 16 + 4 );
+      DPCU_TRY( ctx->scratch.reserve( bytes, false, ctx->stream ) );
+      char *s = static_cast<char *>( ctx->scratch.ptr );
+      DPCU_CUDA( cudaMemcpyAsync( s, lower4, count * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+      DPCU_CUDA( cudaMemcpyAsync( s + count * 16, extent4, count * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+      DPCU_CUDA( cudaMemcpyAsync( s + count * 32, transformIndex, count * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+      lo = reinterpret_cast<float4 const *>( s );
+      ex = reinterpret_cast<float4 const *>( s + count * 16 );
+      ti = reinterpret_cast<uint32_t const *>( s + count * 32 );
+    }
+    else
+    {
+      lo = reinterpret_cast<float4 const *>( lower4 );
+      ex = reinterpret_cast<float4 const *>( extent4 );
+      ti = transformIndex;
+    }
+    dpcu::packObjectsKernel<<<unsigned( dpcu::divUp( count, 256 ) ), 256, 0, ctx->stream>>>(
+      lo, ex, ti, uint32_t( count ), static_cast<float4 *>( ctx->lowerIdx.ptr ) + first,
+      static_cast<float4 *>( ctx->extent.ptr ) + first, static_cast<uint32_t *>( ctx->maxIndex.ptr ) );
+    DPCU_CUDA( cudaGetLastError() );
+    ++ctx->launches;
+    ctx->maxIndexKnown = false;
+    if ( memspace == DPCU_MEM_HOST ) DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuCullSetObjects( dpcuCull *ctx, const float *lower4, const float *extent4, const uint32_t *transformIndex,
+                          size_t n, int memspace )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( n < ( size_t( 1 ) << 32 ), "object count must fit 32 bits" );
+    DPCU_REQUIRE( memspace == DPCU_MEM_HOST || memspace == DPCU_MEM_DEVICE, "bad memspace" );
+    dpcu::DeviceGuard guard( ctx->device );
+    DPCU_TRY( ctx->lowerIdx.reserve( ( n ? n : 1 ) * 16, false, ctx->stream ) );
+    DPCU_TRY( ctx->extent.reserve( ( n ? n : 1 ) * 16, false, ctx->stream ) );
+    ctx->n = n;
+    DPCU_CUDA( cudaMemsetAsync( ctx->maxIndex.ptr, 0, 4, ctx->stream ) );
+    ctx->maxTransformIndex = 0;
+    ctx->maxIndexKnown = true;
+    return dpcuCullSetObjectRange( ctx, 0, n, lower4, extent4, transformIndex, memspace );
+  }
+
+  int dpcuCullGetObjectCount( const dpcuCull *ctx, size_t *n )
+  {
+    DPCU_REQUIRE( ctx && n, "NULL argument" );
+    *n = ctx->n;
+    return DPCU_OK;
+  }
+
+  int dpcuCullSetMatrices( dpcuCull *ctx, const void *matrices, size_t count, size_t strideBytes, int memspace )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( !count || matrices, "matrices is NULL" );
+    DPCU_REQUIRE( strideBytes >= 64 && strideBytes % 4 == 0, "stride must be >= 64 and a multiple of 4" );
+    DPCU_REQUIRE( count < ( size_t( 1 ) << 32 ), "matrix count must fit 32 bits" );
+    DPCU_REQUIRE( memspace == DPCU_MEM_HOST || memspace == DPCU_MEM_DEVICE, "bad memspace" );
+    dpcu::DeviceGuard guard( ctx->device );
+    DPCU_TRY( ctx->mats.reserve( ( count ? count : 1 ) * 64, false, ctx->stream ) );
+    ctx->boundMats = nullptr;
+    ctx->nMats = count;
+    if ( !count ) return DPCU_OK;
+    if ( strideBytes == 64 ) return dpcu::uploadOrCopy( ctx->mats.ptr, matrices, count * 64, memspace, ctx );
+    if ( memspace == DPCU_MEM_HOST )
+    {
+      DPCU_CUDA( cudaMemcpy2DAsync( ctx->mats.ptr, 64, matrices, strideBytes, 64, count, cudaMemcpyHostToDevice, ctx->stream ) );
+      DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    }
+    else
+    {
+      dpcu::gatherStridedKernel<<<unsigned( dpcu::divUp( count * 16, 256 ) ), 256, 0, ctx->stream>>>(
+        static_cast<char const *>( matrices ), strideBytes, uint32_t( count ), static_cast<float *>( ctx->mats.ptr ) );
+      DPCU_CUDA( cudaGetLastError() );
+      ++ctx->launches;
+    }
+    return DPCU_OK;
+  }
+
+  int dpcuCullUpdateMatrices( dpcuCull *ctx, const uint32_t *indices, size_t n, const void *matrices, size_t strideBytes,
+                              int memspace )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( !n || ( indices && matrices ), "NULL argument" );
+    DPCU_REQUIRE( strideBytes >= 64 && strideBytes % 4 == 0, "stride must be >= 64 and a multiple of 4" );
+    DPCU_REQUIRE( !ctx->boundMats, "matrices are bound to external device memory; update them there" );
+    DPCU_REQUIRE( memspace == DPCU_MEM_HOST, "only host source matrices are supported for batched updates" );
+    if ( !n ) return DPCU_OK;
+    dpcu::DeviceGuard guard( ctx->device );
+    // pack [matrices | indices] into pinned staging, skipping indices past the matrix count
+    // (markMatrixDirty ignores those, dp/culling/GroupBitSet.h:140-150)
+    DPCU_TRY( ctx->staging.reserve( n * 68 ) );
+    char *st = static_cast<char *>( ctx->staging.ptr );
+    uint32_t *sidx = reinterpret_cast<uint32_t *>( st + n * 64 );
+    size_t k = 0;
+    for ( size_t i = 0; i < n; ++i )
+    {
+      if ( indices[i] < ctx->nMats )
+      {
+        memcpy( st + k * 64, static_cast<char const *>( matrices ) + size_t( indices[i] ) * strideBytes, 64 );
+        sidx[k++] = indices[i];
+      }
+    }
+    if ( !k ) return DPCU_OK;
+    if ( k != n ) memmove( st + k * 64, sidx, k * 4 );
+    DPCU_TRY( ctx->scratch.reserve( k * 68, false, ctx->stream ) );
+    DPCU_CUDA( cudaMemcpyAsync( ctx->scratch.ptr, st, k * 68, cudaMemcpyHostToDevice, ctx->stream ) );
+    dpcu::scatterMatricesKernel<<<unsigned( dpcu::divUp( k * 4, 256 ) ), 256, 0, ctx->stream>>>(
+      reinterpret_cast<uint32_t const *>( static_cast<char *>( ctx->scratch.ptr ) + k * 64 ),
+      static_cast<float4 const *>( ctx->scratch.ptr ), uint32_t( k ), static_cast<float4 *>( ctx->mats.ptr ) );
+    DPCU_CUDA( cudaGetLastError() );
+    ++ctx->launches;
+    DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );   // staging is reused by the next call
+    return DPCU_OK;
+  }
+
+  int dpcuCullBindMatrices( dpcuCull *ctx, const void *deviceMatrices, size_t count )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( deviceMatrices || !count, "deviceMatrices is NULL" );
+    DPCU_REQUIRE( ( reinterpret_cast<uintptr_t>( deviceMatrices ) & 15 ) == 0, "matrices must be 16-byte aligned" );
+    DPCU_REQUIRE( count < ( size_t( 1 ) << 32 ), "matrix count must fit 32 bits" );
+    ctx->boundMats = static_cast<float const *>( deviceMatrices );
+    ctx->nMats = count;
+    return DPCU_OK;
+  }
+
+  int dpcuCullGetMatrixCount( const dpcuCull *ctx, size_t *count )
+  {
+    DPCU_REQUIRE( ctx && count, "NULL argument" );
+    *count = ctx->nMats;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultCreate( dpcuCull *ctx, dpcuCullResult **out )
+  {
+    DPCU_REQUIRE( ctx && out, "NULL argument" );
+    *out = nullptr;
+    dpcuCullResult *r = new ( std::nothrow ) dpcuCullResult;
+    if ( !r ) return dpcu::fail( DPCU_ERR_OUT_OF_MEMORY, "dpcuCullResultCreate: host allocation failed" );
+    r->ctx = ctx;
+    r->lastStream = ctx->stream;
+    r->next = ctx->results;
+    if ( ctx->results ) ctx->results->prev = r;
+    ctx->results = r;
+    *out = r;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultDestroy( dpcuCullResult *r )
+  {
+    if ( !r ) return DPCU_OK;
+    dpcuCull *ctx = r->ctx;
+    dpcu::DeviceGuard guard( ctx->device );
+    cudaStreamSynchronize( r->lastStream );
+    r->bits.release(); r->chg.release(); r->changed.release(); r->counters.release();
+    if ( r->prev ) r->prev->next = r->next; else ctx->results = r->next;
+    if ( r->next ) r->next->prev = r->prev;
+    delete r;
+    return DPCU_OK;
+  }
+
+  int dpcuCullRun( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, dpcuStream *stream )
+  {
+    DPCU_REQUIRE( ctx && results && viewProjections, "NULL argument" );
+    DPCU_REQUIRE( nViews >= 1 && nViews <= DPCU_MAX_VIEWS, "nViews must be 1..DPCU_MAX_VIEWS" );
+    for ( int v = 0; v < nViews; ++v )
+    {
+      DPCU_REQUIRE( results[v] && results[v]->ctx == ctx, "result does not belong to this context" );
+      for ( int u = 0; u < v; ++u ) DPCU_REQUIRE( results[u] != results[v], "results must be distinct" );
+    }
+    dpcu::DeviceGuard guard( ctx->device );
+    cudaStream_t s = stream ? stream->stream : ctx->stream;
+    if ( s != ctx->stream ) DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );   // uploads happened on the context stream
+    const size_t n = ctx->n;
+    if ( n )
+    {
+      DPCU_TRY( dpcu::refreshMaxIndex( ctx ) );
+      if ( ctx->maxTransformIndex >= ctx->nMats )
+        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: transform index %u out of range (%zu matrices)",
+                           ctx->maxTransformIndex, ctx->nMats );
+    }
+    const size_t nSegs = dpcu::divUp( n, size_t( 1 ) << dpcu::kSegObjectsLog2 );
+    for ( int v = 0; v < nViews; ++v )
+    {
+      dpcuCullResult *r = results[v];
+      if ( r->lastStream != s ) DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+      r->lastStream = s;
+      DPCU_TRY( dpcu::ensureResultCapacity( r, n, s ) );
+      if ( r->n != n )
+      {
+        size_t words = dpcu::divUp( r->n > n ? r->n : n, 32 );
+        dpcu::resizeBitsKernel<<<unsigned( dpcu::divUp( words, 256 ) ), 256, 0, s>>>(
+          static_cast<uint32_t *>( r->bits.ptr ), uint32_t( r->n ), uint32_t( n ), uint32_t( words ) );
+        DPCU_CUDA( cudaGetLastError() );
+        ++ctx->launches;
+        r->n = n;
+      }
+      // zero seg[] | super[] | count (one contiguous block, a few KiB)
+      DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, ( r->nSegsCap + ( r->nSegsCap >> dpcu::kSuperSegsLog2 ) + 2 ) * 4, s ) );
+      r->ran = true;
+    }
+    if ( !n ) return DPCU_OK;
+    int rc = DPCU_OK;
+    switch ( nViews )
+    {
+      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s ); break;
+      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s ); break;
+      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s ); break;
+      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s ); break;
+      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s ); break;
+      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s ); break;
+      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s ); break;
+      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s ); break;
+    }
+    DPCU_TRY( rc );
+    if ( ctx->optChanged )
+    {
+      dpcu::CompactArgs ca;
+      memset( &ca, 0, sizeof ca );
+      for ( int v = 0; v < nViews; ++v )
+      {
+        dpcuCullResult *r = results[v];
+        ca.chg[v] = static_cast<uint32_t const *>( r->chg.ptr );
+        ca.seg[v] = r->segPtr();
+        ca.super[v] = r->superPtr();
+        ca.changed[v] = static_cast<uint32_t *>( r->changed.ptr );
+        ca.count[v] = r->countPtr();
+      }
+      ca.nWords = uint32_t( dpcu::divUp( n, 32 ) );
+      ca.nSegs = uint32_t( nSegs );
+      dim3 grid( ca.nSegs, unsigned( nViews ) );
+      dpcu::compactChangedKernel<<<grid, 256, 0, s>>>( ca );
+      DPCU_CUDA( cudaGetLastError() );
+      ++ctx->launches;
+    }
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultGetBits( dpcuCullResult *r, uint32_t *hostWords, size_t nWords )
+  {
+    DPCU_REQUIRE( r && ( hostWords || !nWords ), "NULL argument" );
+    size_t have = dpcu::divUp( r->n, 32 );
+    DPCU_REQUIRE( nWords >= have, "nWords smaller than ceil(n/32)" );
+    if ( !have ) return DPCU_OK;
+    dpcu::DeviceGuard guard( r->ctx->device );
+    DPCU_CUDA( cudaMemcpyAsync( hostWords, r->bits.ptr, have * 4, cudaMemcpyDeviceToHost, r->lastStream ) );
+    DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultGetChangedCount( dpcuCullResult *r, size_t *count )
+  {
+    DPCU_REQUIRE( r && count, "NULL argument" );
+    *count = 0;
+    if ( !r->ran || !r->n ) return DPCU_OK;
+    if ( !r->ctx->optChanged ) return dpcu::fail( DPCU_ERR_NOT_READY, "changed list disabled (DPCU_CULL_OPT_CHANGED_LIST = 0)" );
+    dpcu::DeviceGuard guard( r->ctx->device );
+    uint32_t c = 0;
+    DPCU_CUDA( cudaMemcpyAsync( &c, r->countPtr(), 4, cudaMemcpyDeviceToHost, r->lastStream ) );
+    DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    *count = c;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultGetChanged( dpcuCullResult *r, uint32_t *hostIndices, size_t capacity, size_t *count )
+  {
+    DPCU_REQUIRE( r && count, "NULL argument" );
+    DPCU_TRY( dpcuCullResultGetChangedCount( r, count ) );
+    size_t c = *count < capacity ? *count : capacity;
+    if ( c )
+    {
+      DPCU_REQUIRE( hostIndices, "hostIndices is NULL" );
+      dpcu::DeviceGuard guard( r->ctx->device );
+      DPCU_CUDA( cudaMemcpyAsync( hostIndices, r->changed.ptr, c * 4, cudaMemcpyDeviceToHost, r->lastStream ) );
+      DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    }
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultIsVisible( dpcuCullResult *r, size_t groupIndex, int *visible )
+  {
+    DPCU_REQUIRE( r && visible, "NULL argument" );
+    *visible = 1;                                  // ResultBitSet::isVisible: true when index >= size
+    if ( groupIndex >= r->n ) return DPCU_OK;
+    dpcu::DeviceGuard guard( r->ctx->device );
+    uint32_t w = 0;
+    DPCU_CUDA( cudaMemcpyAsync( &w, static_cast<uint32_t *>( r->bits.ptr ) + ( groupIndex >> 5 ), 4, cudaMemcpyDeviceToHost, r->lastStream ) );
+    DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    *visible = int( ( w >> ( groupIndex & 31 ) ) & 1u );
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultMoveBit( dpcuCullResult *r, size_t oldIndex, size_t newIndex )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    if ( newIndex >= r->n ) return DPCU_OK;
+    dpcu::DeviceGuard guard( r->ctx->device );
+    uint32_t o = oldIndex < ( size_t( 1 ) << 32 ) ? uint32_t( oldIndex ) : 0xffffffffu;
+    dpcu::moveBitKernel<<<1, 1, 0, r->lastStream>>>( static_cast<uint32_t *>( r->bits.ptr ), uint32_t( r->n ), o, uint32_t( newIndex ) );
+    DPCU_CUDA( cudaGetLastError() );
+    ++r->ctx->launches;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultDevicePointers( dpcuCullResult *r, const uint32_t **bits, size_t *nWords, const uint32_t **changedIndices,
+                                    const uint32_t **changedCount )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    if ( bits ) *bits = static_cast<uint32_t const *>( r->bits.ptr );
+    if ( nWords ) *nWords = dpcu::divUp( r->n, 32 );
+    if ( changedIndices ) *changedIndices = static_cast<uint32_t const *>( r->changed.ptr );
+    if ( changedCount ) *changedCount = r->counters.ptr ? r->countPtr() : nullptr;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultSetPeerBits( dpcuCullResult *r, uint32_t *const *peerBits, int nPeers, size_t wordOffset )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    DPCU_REQUIRE( nPeers >= 0 && nPeers <= dpcu::kMaxPeers, "nPeers must be 0..8" );
+    DPCU_REQUIRE( nPeers == 0 || peerBits, "peerBits is NULL" );
+    DPCU_REQUIRE( wordOffset < ( size_t( 1 ) << 32 ), "wordOffset must fit 32 bits" );
+    for ( int p = 0; p < dpcu::kMaxPeers; ++p ) r->peer[p] = p < nPeers ? peerBits[p] : nullptr;
+    r->nPeers = nPeers;
+    r->peerWordOffset = wordOffset;
+    return DPCU_OK;
+  }
+
+  int dpcuCullGetBoundingBox( dpcuCull *ctx, float *out6 )
+  {
+    DPCU_REQUIRE( ctx && out6, "NULL argument" );
+    dpcu::DeviceGuard guard( ctx->device );
+    const float FMAX = 3.402823466e+38f;
+    float lo[3] = { FMAX, FMAX, FMAX }, hi[3] = { -FMAX, -FMAX, -FMAX };
+    if ( ctx->n )
+    {
+      DPCU_TRY( dpcu::refreshMaxIndex( ctx ) );
+      if ( ctx->maxTransformIndex >= ctx->nMats )
+        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetBoundingBox: transform index %u out of range (%zu matrices)",
+                           ctx->maxTransformIndex, ctx->nMats );
+      DPCU_TRY( ctx->scratch.reserve( 256, false, ctx->stream ) );
+      uint32_t init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+      DPCU_CUDA( cudaMemcpyAsync( ctx->scratch.ptr, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream ) );
+      int grid = int( dpcu::divUp( ctx->n, 256 ) );
+      if ( grid > ctx->smCount * 8 ) grid = ctx->smCount * 8;
+      dpcu::boundingBoxKernel<<<grid, 256, 0, ctx->stream>>>( static_cast<float4 const *>( ctx->lowerIdx.ptr ),
+                                                              static_cast<float4 const *>( ctx->extent.ptr ), ctx->matsPtr(),
+                                                              uint32_t( ctx->n ), static_cast<uint32_t *>( ctx->scratch.ptr ) );
+      DPCU_CUDA( cudaGetLastError() );
+      ++ctx->launches;
+      uint32_t keys[6];
+      DPCU_CUDA( cudaMemcpyAsync( keys, ctx->scratch.ptr, sizeof keys, cudaMemcpyDeviceToHost, ctx->stream ) );
+      DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
+      for ( int k = 0; k < 6; ++k )
+      {
+        uint32_t u = ( keys[k] & 0x80000000u ) ? ( keys[k] & 0x7fffffffu ) : ~keys[k];
+        float f;
+        memcpy( &f, &u, 4 );
+        ( k < 3 ? lo[k] : hi[k - 3] ) = f;
+      }
+    }
+    // Box3f( lower, upper ) = init + update + update  (dp/math/Boxnt.h:215-221)
+    float blo[3] = { FMAX, FMAX, FMAX }, bhi[3] = { -FMAX, -FMAX, -FMAX };
+    for ( int pass = 0; pass < 2; ++pass )
+    {
+      float const *p = pass ? hi : lo;
+      for ( int k = 0; k < 3; ++k )
+      {
+        if ( blo[k] > p[k] ) blo[k] = p[k];
+        if ( bhi[k] < p[k] ) bhi[k] = p[k];
+      }
+    }
+    for ( int k = 0; k < 3; ++k ) { out6[k] = blo[k]; out6[3 + k] = bhi[k]; }
+    return DPCU_OK;
+  }
+
+  int dpcuCullSetOption( dpcuCull *ctx, int option, int value )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    switch ( option )
+    {
+      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 2, "kernel must be 0..2" ); ctx->optKernel = value; break;
+      case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
+      case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
+      case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;
+      default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
+    }
+    return DPCU_OK;
+  }
+
+  int dpcuCullGetOption( const dpcuCull *ctx, int option, int *value )
+  {
+    DPCU_REQUIRE( ctx && value, "NULL argument" );
+    switch ( option )
+    {
+      case DPCU_CULL_OPT_KERNEL:       *value = ctx->optKernel; break;
+      case DPCU_CULL_OPT_FMA:          *value = ctx->optFma; break;
+      case DPCU_CULL_OPT_CHANGED_LIST: *value = ctx->optChanged; break;
+      case DPCU_CULL_OPT_CTAS_PER_SM:  *value = ctx->optCtasPerSm; break;
+      default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
+    }
+    return DPCU_OK;
+  }
+
+  int dpcuCullGetLaunchCount( const dpcuCull *ctx, uint64_t *launches )
+  {
+    DPCU_REQUIRE( ctx && launches, "NULL argument" );
+    *launches = ctx->launches;
+    return DPCU_OK;
+  }
+}
+#endif   // !DPCU_FMA_VARIANT

@@ -1,0 +1,297 @@
+// Transform layer of the C ABI: device mirror of dp::transform::Tree and K1, the level-by-level
+// world-matrix propagation (dp/transform/src/Tree.cpp:133-166, data layout Tree.h:104-128).
+//
+// HBM layout:  local[numNodes], world[numNodes]   4 x float4 per node, 64-byte stride
+//              entries[E]                         uint2 {parent, transform}, levels back to back
+//              dirtyLocal / dirtyWorld            u32 bit words over node indices
+//
+// K1 runs one launch per level.  Four threads cooperate on a node: thread r computes row r of
+// world[t] = local[t] * world[parent] with the reference's association order (a2), so local
+// reads and world writes are 16-byte accesses contiguous across the warp when a level's nodes
+// are contiguous, and the four parent rows are one 64-byte broadcast per node that siblings
+// share through L1/L2.  Compiled with -fmad=false.
+#include "cull_math.cuh"
+#include "dpcu_internal.h"
+
+#include <new>
+#include <vector>
+
+namespace dpcu
+{
+  __device__ __forceinline__ bool testBit( uint32_t const *w, uint32_t i )
+  {
+    return ( w[i >> 5] >> ( i & 31u ) ) & 1u;
+  }
+
+  __global__ void __launch_bounds__( 256 ) treeLevelKernel( uint2 const *__restrict__ entries, uint32_t count,
+                                                            float4 const *__restrict__ local, float4 *world,
+                                                            uint32_t const *__restrict__ dirtyLocal, uint32_t *dirtyWorld )
+  {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t e = t >> 2, r = t & 3u;
+    if ( e >= count ) return;
+    const uint2 pe = __ldg( entries + e );
+    const uint32_t parent = pe.x, node = pe.y;
+    // Tree.cpp:155 - parent bits were set by earlier launches; this launch only ORs bits of its own level
+    if ( !( testBit( dirtyWorld, parent ) || testBit( dirtyLocal, node ) ) ) return;
+    const float4 a  = ldStream( local + 4ull * node + r );
+    float4 const *pw = world + 4ull * parent;
+    const float4 b0 = pw[0], b1 = pw[1], b2 = pw[2], b3 = pw[3];
+    world[4ull * node + r] = vecMulMat( a, b0, b1, b2, b3 );      // Tree.cpp:157, Matmnt.h:1381-1415
+    if ( r == 0 ) atomicOr( dirtyWorld + ( node >> 5 ), 1u << ( node & 31u ) );   // Tree.cpp:158
+  }
+
+  __global__ void treeInitNodesKernel( float4 *local, float4 *world, uint32_t *dirtyLocal, uint32_t first, uint32_t count )
+  {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( t >= count * 4u ) return;
+    const uint32_t node = first + ( t >> 2 ), r = t & 3u;
+    const float4 row = make_float4( r == 0 ? 1.f : 0.f, r == 1 ? 1.f : 0.f, r == 2 ? 1.f : 0.f, r == 3 ? 1.f : 0.f );
+    local[4ull * node + r] = row;
+    world[4ull * node + r] = row;
+    if ( r == 0 ) atomicOr( dirtyLocal + ( node >> 5 ), 1u << ( node & 31u ) );
+  }
+
+  __global__ void treeMarkRangeKernel( uint32_t *dirtyLocal, uint32_t first, uint32_t count )
+  {
+    // one thread per word touched by [first, first+count)
+    const uint32_t w0 = first >> 5;
+    const uint32_t w  = w0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t lo = uint64_t( w ) << 5, hi = lo + 32, end = uint64_t( first ) + count;
+    if ( lo >= end ) return;
+    uint32_t mask = ~0u;
+    if ( first > lo ) mask &= ~0u << ( first - lo );
+    if ( end < hi )   mask &= ~0u >> ( hi - end );
+    atomicOr( dirtyLocal + w, mask );
+  }
+
+  __global__ void treeScatterLocalsKernel( uint32_t const *indices, float4 const *packed, uint32_t n, uint32_t numNodes,
+                                           float4 *local, uint32_t *dirtyLocal )
+  {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( t >= n * 4u ) return;
+    const uint32_t node = indices[t >> 2], r = t & 3u;
+    if ( node >= numNodes ) return;
+    local[4ull * node + r] = packed[t];
+    if ( r == 0 ) atomicOr( dirtyLocal + ( node >> 5 ), 1u << ( node & 31u ) );
+  }
+}
+
+struct dpcuTree
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  dpcu::DeviceArray local, world, entries, dirtyLocal, dirtyWorld, scratch;
+  size_t       numNodes = 0;
+  size_t       numEntries = 0;
+  std::vector<uint32_t> levelOffsets;
+  uint64_t     launches = 0;
+  cudaStream_t lastStream = nullptr;
+};
+
+extern "C"
+{
+  int dpcuTreeCreate( dpcuTree **out, int device )
+  {
+    DPCU_REQUIRE( out, "out is NULL" );
+    *out = nullptr;
+    DPCU_TRY( dpcu::requireDevice() );
+    int count = 0;
+    DPCU_CUDA( cudaGetDeviceCount( &count ) );
+    DPCU_REQUIRE( device >= 0 && device < count, "device index out of range" );
+    dpcu::DeviceGuard guard( device );
+    dpcuTree *t = new ( std::nothrow ) dpcuTree;
+    if ( !t ) return dpcu::fail( DPCU_ERR_OUT_OF_MEMORY, "dpcuTreeCreate: host allocation failed" );
+    t->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags( &t->stream, cudaStreamNonBlocking );
+    if ( e != cudaSuccess ) { delete t; return dpcu::failCuda( e, "cudaStreamCreateWithFlags", __FILE__, __LINE__ ); }
+    t->lastStream = t->stream;
+    *out = t;
+    return DPCU_OK;
+  }
+
+  int dpcuTreeDestroy( dpcuTree *t )
+  {
+    if ( !t ) return DPCU_OK;
+    dpcu::DeviceGuard guard( t->device );
+    cudaStreamSynchronize( t->stream );
+    if ( t->lastStream != t->stream ) cudaStreamSynchronize( t->lastStream );
+    t->local.release(); t->world.release(); t->entries.release(); t->dirtyLocal.release(); t->dirtyWorld.release(); t->scratch.release();
+    cudaStreamDestroy( t->stream );
+    delete t;
+    return DPCU_OK;
+  }
+
+  int dpcuTreeSetTopology( dpcuTree *t, const uint32_t *entries, const uint32_t *levelOffsets, int numLevels, size_t numNodes )
+  {
+    DPCU_REQUIRE( t, "tree is NULL" );
+    DPCU_REQUIRE( numLevels >= 0 && ( numLevels == 0 || ( entries && levelOffsets ) ), "NULL topology" );
+    DPCU_REQUIRE( numNodes >= 1 && numNodes < ( size_t( 1 ) << 30 ), "numNodes must be in [1, 2^30)" );
+    DPCU_REQUIRE( numNodes >= t->numNodes, "the node array never shrinks (Tree::resizeDataStructures only grows, Tree.cpp:117-126)" );
+    size_t numEntries = numLevels ? levelOffsets[numLevels] : 0;
+    for ( int l = 0; l < numLevels; ++l ) DPCU_REQUIRE( levelOffsets[l] <= levelOffsets[l + 1], "levelOffsets must be ascending" );
+    for ( size_t e = 0; e < numEntries; ++e )
+    {
+      // Tree::addTransform throws for an invalid parent (Tree.cpp:56-59)
+      if ( entries[2 * e] >= numNodes || entries[2 * e + 1] >= numNodes || entries[2 * e + 1] == 0 )
+        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuTreeSetTopology: entry %zu {%u,%u} out of range", e, entries[2 * e], entries[2 * e + 1] );
+    }
+    dpcu::DeviceGuard guard( t->device );
+    cudaStream_t s = t->stream;
+    size_t oldNodes = t->numNodes;
+    size_t oldWords = dpcu::divUp( oldNodes, 32 ), newWords = dpcu::divUp( numNodes, 32 );
+    DPCU_TRY( t->local.reserve( numNodes * 64, true, s ) );
+    DPCU_TRY( t->world.reserve( numNodes * 64, true, s ) );
+    size_t oldDirtyCap = t->dirtyLocal.capacity;
+    DPCU_TRY( t->dirtyLocal.reserve( newWords * 4, true, s ) );
+    DPCU_TRY( t->dirtyWorld.reserve( newWords * 4, true, s ) );
+    if ( t->dirtyLocal.capacity > oldDirtyCap )
+    {
+      size_t keep = oldDirtyCap < oldWords * 4 ? oldDirtyCap : oldWords * 4;
+      DPCU_CUDA( cudaMemsetAsync( static_cast<char *>( t->dirtyLocal.ptr ) + keep, 0, t->dirtyLocal.capacity - keep, s ) );
+      DPCU_CUDA( cudaMemsetAsync( static_cast<char *>( t->dirtyWorld.ptr ) + keep, 0, t->dirtyWorld.capacity - keep, s ) );
+    }
+    if ( numNodes > oldNodes )
+    {
+      uint32_t cnt = uint32_t( numNodes - oldNodes );
+      dpcu::treeInitNodesKernel<<<unsigned( dpcu::divUp( size_t( cnt ) * 4, 256 ) ), 256, 0, s>>>(
+        static_cast<float4 *>( t->local.ptr ), static_cast<float4 *>( t->world.ptr ), static_cast<uint32_t *>( t->dirtyLocal.ptr ),
+        uint32_t( oldNodes ), cnt );
+      DPCU_CUDA( cudaGetLastError() );
+      ++t->launches;
+    }
+    DPCU_TRY( t->entries.reserve( ( numEntries ? numEntries : 1 ) * 8, false, s ) );
+    if ( numEntries )
+    {
+      DPCU_CUDA( cudaMemcpyAsync( t->entries.ptr, entries, numEntries * 8, cudaMemcpyHostToDevice, s ) );
+    }
+    DPCU_CUDA( cudaStreamSynchronize( s ) );
+    t->numNodes = numNodes;
+    t->numEntries = numEntries;
+    t->levelOffsets.assign( levelOffsets, levelOffsets + ( numLevels ? numLevels + 1 : 0 ) );
+    return DPCU_OK;
+  }
+
+  int dpcuTreeMarkDirty( dpcuTree *t, size_t first, size_t count )
+  {
+    DPCU_REQUIRE( t, "tree is NULL" );
+    DPCU_REQUIRE( first + count <= t->numNodes, "range exceeds node count" );
+    if ( !count ) return DPCU_OK;
+    dpcu::DeviceGuard guard( t->device );
+    size_t words = ( ( first + count - 1 ) >> 5 ) - ( first >> 5 ) + 1;
+    dpcu::treeMarkRangeKernel<<<unsigned( dpcu::divUp( words, 256 ) ), 256, 0, t->stream>>>(
+      static_cast<uint32_t *>( t->dirtyLocal.ptr ), uint32_t( first ), uint32_t( count ) );
+    DPCU_CUDA( cudaGetLastError() );
+    ++t->launches;
+    return DPCU_OK;
+  }
+
+  int dpcuTreeSetLocals( dpcuTree *t, size_t first, size_t count, const float *matrices, int memspace )
+  {
+    DPCU_REQUIRE( t, "tree is NULL" );
+    DPCU_REQUIRE( first + count <= t->numNodes, "range exceeds node count" );
+    DPCU_REQUIRE( matrices || !count, "matrices is NULL" );
+    DPCU_REQUIRE( memspace == DPCU_MEM_HOST || memspace == DPCU_MEM_DEVICE, "bad memspace" );
+    if ( !count ) return DPCU_OK;
+    dpcu::DeviceGuard guard( t->device );
+    char *dst = static_cast<char *>( t->local.ptr ) + first * 64;
+    DPCU_CUDA( cudaMemcpyAsync( dst, matrices, count * 64, memspace == DPCU_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, t->stream ) );
+    DPCU_TRY( dpcuTreeMarkDirty( t, first, count ) );
+    if ( memspace == DPCU_MEM_HOST ) DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuTreeUpdateLocals( dpcuTree *t, const uint32_t *indices, size_t n, const float *matrices, int memspace )
+  {
+    DPCU_REQUIRE( t, "tree is NULL" );
+    DPCU_REQUIRE( !n || ( indices && matrices ), "NULL argument" );
+    DPCU_REQUIRE( memspace == DPCU_MEM_HOST, "scattered updates take host memory (indices and matrices)" );
+    DPCU_REQUIRE( n < ( size_t( 1 ) << 30 ), "too many updates" );
+    if ( !n ) return DPCU_OK;
+    for ( size_t i = 0; i < n; ++i ) DPCU_REQUIRE( indices[i] < t->numNodes, "node index out of range" );
+    dpcu::DeviceGuard guard( t->device );
+    DPCU_TRY( t->scratch.reserve( n * 68, false, t->stream ) );
+    char *s = static_cast<char *>( t->scratch.ptr );
+    DPCU_CUDA( cudaMemcpyAsync( s, matrices, n * 64, cudaMemcpyHostToDevice, t->stream ) );
+    DPCU_CUDA( cudaMemcpyAsync( s + n * 64, indices, n * 4, cudaMemcpyHostToDevice, t->stream ) );
+    dpcu::treeScatterLocalsKernel<<<unsigned( dpcu::divUp( n * 4, 256 ) ), 256, 0, t->stream>>>(
+      reinterpret_cast<uint32_t const *>( s + n * 64 ), reinterpret_cast<float4 const *>( s ), uint32_t( n ), uint32_t( t->numNodes ),
+      static_cast<float4 *>( t->local.ptr ), static_cast<uint32_t *>( t->dirtyLocal.ptr ) );
+    DPCU_CUDA( cudaGetLastError() );
+    ++t->launches;
+    DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuTreeCompute( dpcuTree *t, dpcuStream *stream )
+  {
+    DPCU_REQUIRE( t, "tree is NULL" );
+    DPCU_REQUIRE( t->numNodes >= 1, "no topology set" );
+    dpcu::DeviceGuard guard( t->device );
+    cudaStream_t s = stream ? stream->stream : t->stream;
+    if ( s != t->stream ) DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
+    if ( t->lastStream != s ) DPCU_CUDA( cudaStreamSynchronize( t->lastStream ) );
+    t->lastStream = s;
+    size_t words = dpcu::divUp( t->numNodes, 32 );
+    // the previous compute's published set is dropped now (the reference clears it right after notifying, Tree.cpp:163-164)
+    DPCU_CUDA( cudaMemsetAsync( t->dirtyWorld.ptr, 0, words * 4, s ) );
+    size_t levels = t->levelOffsets.empty() ? 0 : t->levelOffsets.size() - 1;
+    for ( size_t l = 0; l < levels; ++l )
+    {
+      uint32_t first = t->levelOffsets[l], count = t->levelOffsets[l + 1] - first;
+      if ( !count ) continue;
+      dpcu::treeLevelKernel<<<unsigned( dpcu::divUp( size_t( count ) * 4, 256 ) ), 256, 0, s>>>(
+        static_cast<uint2 const *>( t->entries.ptr ) + first, count, static_cast<float4 const *>( t->local.ptr ),
+        static_cast<float4 *>( t->world.ptr ), static_cast<uint32_t const *>( t->dirtyLocal.ptr ), static_cast<uint32_t *>( t->dirtyWorld.ptr ) );
+      DPCU_CUDA( cudaGetLastError() );
+      ++t->launches;
+    }
+    DPCU_CUDA( cudaMemsetAsync( t->dirtyLocal.ptr, 0, words * 4, s ) );   // Tree.cpp:163
+    return DPCU_OK;
+  }
+
+  int dpcuTreeWorldDevicePointer( dpcuTree *t, const float **deviceMatrices, size_t *numNodes )
+  {
+    DPCU_REQUIRE( t && deviceMatrices, "NULL argument" );
+    *deviceMatrices = static_cast<float const *>( t->world.ptr );
+    if ( numNodes ) *numNodes = t->numNodes;
+    return DPCU_OK;
+  }
+
+  int dpcuTreeLocalDevicePointer( dpcuTree *t, float **deviceMatrices, size_t *numNodes )
+  {
+    DPCU_REQUIRE( t && deviceMatrices, "NULL argument" );
+    *deviceMatrices = static_cast<float *>( t->local.ptr );
+    if ( numNodes ) *numNodes = t->numNodes;
+    return DPCU_OK;
+  }
+
+  int dpcuTreeGetWorld( dpcuTree *t, size_t first, size_t count, float *hostMatrices )
+  {
+    DPCU_REQUIRE( t && ( hostMatrices || !count ), "NULL argument" );
+    DPCU_REQUIRE( first + count <= t->numNodes, "range exceeds node count" );
+    if ( !count ) return DPCU_OK;
+    dpcu::DeviceGuard guard( t->device );
+    DPCU_CUDA( cudaMemcpyAsync( hostMatrices, static_cast<char *>( t->world.ptr ) + first * 64, count * 64, cudaMemcpyDeviceToHost, t->lastStream ) );
+    DPCU_CUDA( cudaStreamSynchronize( t->lastStream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuTreeGetDirtyWorld( dpcuTree *t, uint32_t *hostWords, size_t nWords )
+  {
+    DPCU_REQUIRE( t && ( hostWords || !nWords ), "NULL argument" );
+    size_t have = dpcu::divUp( t->numNodes, 32 );
+    DPCU_REQUIRE( nWords >= have, "nWords smaller than ceil(numNodes/32)" );
+    dpcu::DeviceGuard guard( t->device );
+    DPCU_CUDA( cudaMemcpyAsync( hostWords, t->dirtyWorld.ptr, have * 4, cudaMemcpyDeviceToHost, t->lastStream ) );
+    DPCU_CUDA( cudaStreamSynchronize( t->lastStream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuTreeGetLaunchCount( const dpcuTree *t, uint64_t *launches )
+  {
+    DPCU_REQUIRE( t && launches, "NULL argument" );
+    *launches = t->launches;
+    return DPCU_OK;
+  }
+}

@@ -1,0 +1,379 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against
+  - the golden vectors produced by the compiled reference (tests/golden),
+  - the C restatement (oracle/libdporacle.so) on the same seeded inputs,
+  - the compiled reference itself when oracle/_ref/libdpref.so travelled to the box.
+Bit-exact: visibility words and changed lists must be identical (integer compare)."""
+import numpy as np
+import pytest
+
+from pipeline_b200 import scenes
+from tests import cases
+from tests.engines import CudaEngine, PortEngine, RefEngine, run_lifecycle
+
+pytestmark = pytest.mark.gpu
+
+
+def popcount(words):
+    return int(np.unpackbits(words.view(np.uint8)).sum())
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from pipeline_b200 import capi
+    assert capi.device_count() >= 1
+    return capi
+
+
+def test_device_is_blackwell(capi):
+    info = capi.device_info(0)
+    assert info["cc"][0] == 10, info
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_grid_known_answer(capi, golden):
+    g = golden("grid32")
+    lower4, extent4, upper4, mats, tidx, vp = scenes.grid_scene(32)
+    e = CudaEngine()
+    e.add(lower4, upper4, tidx)
+    e.set_matrices(mats.reshape(-1))
+    bits, changed = e.cull(vp)
+    assert popcount(bits) == 3100 and len(changed) == 29668
+    assert np.array_equal(bits, g["bits"])
+    assert np.array_equal(changed, g["changed"])
+    bits2, changed2 = e.cull(vp)
+    assert len(changed2) == 0 and np.array_equal(bits2, bits)
+    assert np.array_equal(e.bounding_box(), g["bbox"])
+    e.close()
+
+
+def test_random_scene_moving_camera(capi, golden):
+    g = golden("random20k")
+    lower4, extent4, upper4, mats, tidx = cases.random_case()
+    e = CudaEngine()
+    e.add(lower4, upper4, tidx)
+    e.set_matrices(mats.reshape(-1))
+    for k, vp in enumerate(cases.frames()):
+        bits, changed = e.cull(vp)
+        assert np.array_equal(bits, g["bits%d" % k]), "frame %d bits" % k
+        assert np.array_equal(changed, g["changed%d" % k]), "frame %d changed list" % k
+    assert np.array_equal(e.bounding_box(), g["bbox"])
+    e.close()
+
+
+def test_special_values(capi, golden):
+    g = golden("special4k")
+    lower4, extent4, upper4, mats, tidx, vps = cases.special_case()
+    e = CudaEngine()
+    e.add(lower4, upper4, tidx)
+    e.set_matrices(mats.reshape(-1))
+    for k, vp in enumerate(vps):
+        bits, changed = e.cull(vp)
+        assert np.array_equal(bits, g["bits%d" % k])
+        assert np.array_equal(changed, g["changed%d" % k])
+    e.close()
+
+
+def test_gather_and_stride(capi, golden):
+    g = golden("gather5k")
+    lower4, extent4, upper4, raw, tidx, stride = cases.gather_case()
+    e = CudaEngine()
+    e.add(lower4, upper4, tidx)
+    e.set_matrices(raw.reshape(-1), stride, len(raw))
+    bits, changed = e.cull(scenes.camera_c2())
+    assert np.array_equal(bits, g["bits"])
+    assert np.array_equal(changed, g["changed"])
+    assert np.array_equal(e.bounding_box(), g["bbox"])
+    e.close()
+
+
+def test_lifecycle(capi, golden):
+    g = golden("lifecycle")
+    lower4, extent4, upper4, mats, tidx = cases.random_case(5000, seed=0x11FE)
+    e = CudaEngine()
+    res = run_lifecycle(e, cases.lifecycle_script(), lower4, upper4, mats, cases.frames())
+    for k, (bits, changed, n) in enumerate(res):
+        assert n == int(g["count%d" % k])
+        assert np.array_equal(bits, g["bits%d" % k]), "step %d bits" % k
+        assert np.array_equal(changed, g["changed%d" % k]), "step %d changed" % k
+    e.close()
+
+
+def test_tree_golden(capi, golden):
+    g = golden("tree")
+    entries, offsets, n_nodes, local = cases.tree_case()
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    t.set_locals(0, local)
+    t.compute()
+    assert np.array_equal(t.world().view(np.uint32), g["world0"].view(np.uint32))
+    assert np.array_equal(t.dirty_world(), g["dirty0"])
+    for frame in (1, 2, 3):
+        idx, m = cases.tree_updates(n_nodes, frame)
+        t.update_locals(idx, m)
+        t.compute()
+        assert np.array_equal(t.world().view(np.uint32), g["world%d" % frame].view(np.uint32)), "frame %d world" % frame
+        assert np.array_equal(t.dirty_world(), g["dirty%d" % frame]), "frame %d dirty set" % frame
+    t.close()
+
+
+# ------------------------------------------------------------------ oracle on the same seeded inputs
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 256, 257, 8191, 8192, 8193, 100003])
+def test_sizes_vs_port(capi, port, n):
+    lower4, extent4, upper4, mats, tidx = cases.random_case(max(n, 1))
+    lower4, extent4, upper4, tidx = lower4[:n], extent4[:n], upper4[:n], tidx[:n]
+    c, p = CudaEngine(), PortEngine(port)
+    for e in (c, p):
+        e.add(lower4, upper4, tidx)
+        e.set_matrices(mats.reshape(-1))
+    for vp in cases.frames(3):
+        cb, cc = c.cull(vp)
+        pb, pc = p.cull(vp)
+        assert np.array_equal(cb, pb)
+        assert np.array_equal(cc, pc)
+    if n:
+        assert np.array_equal(c.bounding_box(), p.bounding_box())
+    c.close()
+
+
+def test_c2_one_million_vs_port_and_reference(capi, port):
+    """BASELINE config C2: 2^20 random objects, one matrix each, single frustum."""
+    from oracle.loader import Reference
+    n = 1 << 20
+    lower4, extent4, upper4, mats, tidx = scenes.random_objects(scenes.SEED_C2, 0, n)
+    engines = [CudaEngine(), PortEngine(port)]
+    if Reference.available():
+        engines.append(RefEngine())
+    for e in engines:
+        e.add(lower4, upper4, tidx)
+        e.set_matrices(mats.reshape(-1))
+    for vp in cases.frames(4):
+        outs = [e.cull(vp) for e in engines]
+        for b, c in outs[1:]:
+            assert np.array_equal(outs[0][0], b)
+            assert np.array_equal(outs[0][1], c)
+        assert 0.02 < popcount(outs[0][0]) / n < 0.5
+    boxes = [e.bounding_box() for e in engines]
+    for b in boxes[1:]:
+        assert np.array_equal(boxes[0], b)
+    for e in engines:
+        e.close()
+
+
+def test_special_values_fuzz_vs_port(capi, port):
+    for seed in range(40, 52):
+        lower4, extent4, upper4, mats, tidx, vps = cases.special_case(3000, seed=seed)
+        c, p = CudaEngine(), PortEngine(port)
+        for e in (c, p):
+            e.add(lower4, upper4, tidx)
+            e.set_matrices(mats.reshape(-1))
+        for vp in vps + [scenes.camera_c2()]:
+            cb, cc = c.cull(vp)
+            pb, pc = p.cull(vp)
+            assert np.array_equal(cb, pb), seed
+            assert np.array_equal(cc, pc), seed
+        c.close()
+
+
+def test_multi_view_equals_single_views(capi, port):
+    """C4 style: six cube-map frusta in one pass == six independent culls == oracle."""
+    n = 50000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C4)
+    vps = scenes.cube_map_cameras()
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    multi = [ctx.result_create() for _ in range(6)]
+    ctx.run(multi, vps)
+    seen = np.zeros((n + 31) // 32, np.uint32)
+    for v in range(6):
+        want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vps[v])
+        assert np.array_equal(multi[v].bits(), want), "view %d" % v
+        res = port.result_resize(np.zeros(0, np.uint32), 0, n)
+        assert np.array_equal(multi[v].changed(), port.update_changed(want, res, n))
+        single = ctx.result_create()
+        ctx.run([single], vps[v])
+        assert np.array_equal(single.bits(), want)
+        single.close()
+        seen |= want
+    assert popcount(seen) > 0.9 * n          # six 90-degree faces cover (almost) everything
+    for r in multi:
+        r.close()
+    ctx.close()
+
+
+def test_matrix_updates_vs_port(capi, port):
+    lower4, extent4, upper4, mats, tidx = cases.random_case(4096)
+    mats = mats.copy()
+    c, p = CudaEngine(), PortEngine(port)
+    for e in (c, p):
+        e.add(lower4, upper4, tidx)
+        e.set_matrices(mats.reshape(-1))
+    vp = scenes.camera_c2()
+    c.cull(vp), p.cull(vp)
+    idx = np.arange(0, 4096, 7, dtype=np.uint32)
+    mats[idx.astype(np.int64), 3, 2] -= np.float32(300.0)
+    c.matrices_changed(np.concatenate([idx, np.array([999999], np.uint32)]))   # out-of-range index is ignored (GroupBitSet.h:140-150)
+    cb, cc = c.cull(vp)
+    pb, pc = p.cull(vp)
+    assert np.array_equal(cb, pb) and np.array_equal(cc, pc) and len(cc) > 0
+    c.close()
+
+
+def test_fma_mode_reports_disagreements(capi, port):
+    """The -fmad=true fast mode is NOT the product; it must exist only as a reporting option and its
+    disagreements with the exact path are confined to boundary objects."""
+    n = 1 << 18
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    exact, fast = ctx.result_create(), ctx.result_create()
+    vp = scenes.camera_c2()
+    ctx.run([exact], vp)
+    ctx.set_option(capi.OPT_FMA, 1)
+    ctx.run([fast], vp)
+    ctx.set_option(capi.OPT_FMA, 0)
+    want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vp)
+    assert np.array_equal(exact.bits(), want)
+    diff = popcount(fast.bits() ^ want)
+    assert diff < n // 1000, diff
+    print("fma fast mode: %d of %d objects disagree with the exact path" % (diff, n))
+    exact.close(), fast.close(), ctx.close()
+
+
+def test_error_behaviour(capi):
+    ctx = capi.Cull(0)
+    lower4, extent4, upper4, mats, tidx = cases.random_case(100)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats[:50].reshape(-1))            # indices 50..99 out of range
+    r = ctx.result_create()
+    with pytest.raises(capi.DpcuError) as e:
+        ctx.run([r], scenes.camera_c2())
+    assert "out of range" in str(e.value)
+    with pytest.raises(capi.DpcuError):
+        ctx.run([r, r], np.stack([scenes.camera_c2()] * 2))   # results must be distinct
+    with pytest.raises(capi.DpcuError):
+        ctx.close()                                     # results still alive
+    assert r.is_visible(5) and r.is_visible(10 ** 6)    # never culled / beyond size: visible (ResultBitSet.h:69-76)
+    r.close()
+    ctx.close()
+
+
+def test_result_device_pointers_and_is_visible(capi, port):
+    lower4, extent4, upper4, mats, tidx = cases.random_case(1000)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    r = ctx.result_create()
+    ctx.run([r], scenes.camera_c2())
+    want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), scenes.camera_c2())
+    for i in (0, 1, 31, 32, 500, 999):
+        assert r.is_visible(i) == bool((want[i >> 5] >> (i & 31)) & 1)
+    d = r.device_pointers()
+    assert d["bits"] and d["changed"] and d["count"] and d["n_words"] == 32
+    r.close(), ctx.close()
+
+
+# ------------------------------------------------------------------ transform tree
+def test_tree_vs_port_large(capi, port):
+    entries, offsets, n_nodes = scenes.hierarchy_topology((64, 1024, 16384, 262144))
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=0)
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    t.set_locals(0, local)
+    nw = (n_nodes + 31) // 32
+    world = np.zeros_like(local)
+    world[0] = np.eye(4, dtype=np.float32)
+    dl = np.full(nw, 0xFFFFFFFF, np.uint32)
+    dw = np.zeros(nw, np.uint32)
+    for frame in range(3):
+        if frame:
+            upd = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=frame)
+            if frame == 1:                               # everything dirty, contiguous upload
+                local[1:] = upd
+                t.set_locals(1, upd)
+                dl[:] = 0xFFFFFFFF
+            else:                                        # only an inner level dirty: descendants must follow
+                a, b = 1 + 64, 1 + 64 + 1024
+                local[a:b] = upd[a - 1:b - 1]
+                t.update_locals(np.arange(a, b, dtype=np.uint32), local[a:b])
+                for i in range(a, b):
+                    dl[i >> 5] |= np.uint32(1 << (i & 31))
+        t.compute()
+        dw[:] = 0
+        port.tree_compute(local, world, entries, offsets, dl, dw)
+        assert np.array_equal(t.world().view(np.uint32), world.view(np.uint32)), frame
+        got = t.dirty_world()
+        got[-1] &= np.uint32((1 << (n_nodes % 32)) - 1) if n_nodes % 32 else np.uint32(0xFFFFFFFF)
+        assert np.array_equal(got, dw), frame
+    t.close()
+
+
+def test_tree_feeds_cull_zero_copy(capi, port):
+    """Config C3 in miniature: propagate on the device, cull straight out of the tree's world matrices."""
+    entries, offsets, n_nodes = scenes.hierarchy_topology((8, 64, 512, 4096))
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    n = 4096
+    first_leaf = n_nodes - n
+    lower4, extent4, upper4, _, _ = cases.random_case(n)
+    tidx = np.arange(first_leaf, n_nodes, dtype=np.uint32)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    r = ctx.result_create()
+    world = np.zeros_like(local)
+    world[0] = np.eye(4, dtype=np.float32)
+    nw = (n_nodes + 31) // 32
+    res = np.zeros(0, np.uint32)
+    res_n = 0
+    vp = scenes.mat_mul(scenes.make_look_at((0, 0, 150), (0, 0, 0), (0, 1, 0)), scenes.make_perspective(40.0, 1.3, 1.0, 500.0))
+    for frame in range(3):
+        local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=frame * 10)
+        t.set_locals(0, local)
+        t.compute()
+        ptr, cnt = t.world_ptr()
+        ctx.bind_matrices(ptr, cnt)
+        ctx.run([r], vp)
+        dl = np.full(nw, 0xFFFFFFFF, np.uint32)
+        dw = np.zeros(nw, np.uint32)
+        port.tree_compute(local, world, entries, offsets, dl, dw)
+        want = port.cull_bits(lower4, extent4, tidx, world.reshape(-1), vp)
+        if res_n != n:
+            res = port.result_resize(res, res_n, n)
+            res_n = n
+        want_changed = port.update_changed(want, res, n)
+        assert np.array_equal(r.bits(), want), frame
+        assert np.array_equal(r.changed(), want_changed), frame
+    assert 0 < popcount(want) < n
+    r.close(), ctx.close(), t.close()
+
+
+# ------------------------------------------------------------------ dp/cuda layer
+def test_buffers_streams_events(capi):
+    s = capi.Stream()
+    e0, e1 = capi.Event(), capi.Event()
+    b = capi.Buffer(1 << 20)
+    h = capi.HostBuffer(1 << 20)
+    a = h.array(np.uint32)
+    a[:] = np.arange(len(a), dtype=np.uint32)
+    e0.record(s)
+    b.upload(a, stream=s)
+    out = np.zeros_like(a)
+    b.download(out, stream=s)
+    e1.record(s)
+    s.sync()
+    assert s.completed()
+    assert np.array_equal(out, a)
+    assert e0.elapsed_ms(e1) >= 0.0
+    b.fill(0xAB, 16, 4)
+    small = np.zeros(6, np.uint32)
+    b.download(small)
+    assert small[0] == 0 and small[1] == 0xABABABAB and small[4] == 0xABABABAB and small[5] == 5
+    with pytest.raises(capi.DpcuError):
+        b.upload(np.zeros((1 << 20) + 4, np.uint8))
+    for x in (b, h, e0, e1, s):
+        x.close()

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Developer probe (not the contract bench): device-resident cull timings for a few sizes / variants."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pipeline_b200 import capi, scenes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1 << 26)
+    ap.add_argument("--views", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--fma", type=int, default=0)
+    ap.add_argument("--changed", type=int, default=1)
+    ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
+    a = ap.parse_args()
+    n = a.n
+    lo, ex, mt = capi.Buffer(n * 16), capi.Buffer(n * 16), capi.Buffer(n * 64)
+    capi.scene_generate(scenes.SEED_C4, 0, n, 0, lo.ptr, ex.ptr, mt.ptr)
+    capi.device_sync()
+    ctx = capi.Cull(0)
+    ctx.set_objects(lo.ptr, ex.ptr, None, capi.MEM_DEVICE, n=n)
+    ctx.bind_matrices(mt.ptr, n)
+    ctx.set_option(capi.OPT_KERNEL, a.kernel)
+    ctx.set_option(capi.OPT_CTAS_PER_SM, a.ctas)
+    ctx.set_option(capi.OPT_FMA, a.fma)
+    ctx.set_option(capi.OPT_CHANGED_LIST, a.changed)
+    res = [ctx.result_create() for _ in range(a.views)]
+    cams = scenes.cube_map_cameras() if a.views > 1 else None
+    s = capi.Stream()
+    e0, e1 = capi.Event(), capi.Event()
+
+    def vps(f):
+        if a.views > 1:
+            return cams[:a.views]
+        return scenes.camera_c2() if a.static else scenes.orbit_camera(f)
+
+    for f in range(3):
+        ctx.run(res, vps(f), s)
+    s.sync()
+    times = []
+    for f in range(a.iters):
+        e0.record(s)
+        ctx.run(res, vps(3 + f), s)
+        e1.record(s)
+        s.sync()
+        times.append(e0.elapsed_ms(e1))
+    t = np.median(times)
+    bytes_alg = n * (96 + 0.25 * a.views) + 4 * sum(r.changed_count() for r in res)
+    vis = int(np.unpackbits(res[0].bits().view(np.uint8)).sum())
+    print("n=%d views=%d kernel=%d ctas=%d fma=%d changed=%d: median %.4f ms (min %.4f) -> %.2f Gobj/s, %.0f GB/s algorithmic; visible %.1f%% changed %d"
+          % (n, a.views, a.kernel, a.ctas, a.fma, a.changed, t, min(times), n / t / 1e6, bytes_alg / t / 1e6, 100.0 * vis / n, res[0].changed_count()))
+
+
+if __name__ == "__main__":
+    main()
