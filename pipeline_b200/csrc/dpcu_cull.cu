@@ -12,12 +12,12 @@
 //   mats[m]      4 x float4 per matrix, row-major, 64-byte stride                 64 B / matrix
 //   per result:  bits[ceil(n/32)] u32 (previous visibility, updated in place),
 //                chg[ceil(n/32)]  u32 (bits that flipped in the last cull),
-//                changed[n] u32 (ascending group indices), seg[]/super[] u32 changed-counts
-//                per 8192 / 1 Mi objects, count u32.
+//                changed[n] u32 (ascending group indices), seg[] u32 changed-counts per 8192
+//                objects (exclusive prefix after the cull; seg[nSegs] = total).
 //
 // One cull = memset(counters) -> cull kernel (one pass over the objects for up to 8 views:
-// ballot -> word, XOR with the previous word, popc into the segment counters) -> compaction
-// kernel (segment-ordered expansion of the flipped bits into the changed list).
+// ballot -> word, XOR with the previous word, popc into the segment counters, last CTA scans the
+// counters) -> compaction kernel (segment-ordered expansion of the flipped bits into the list).
 //
 // This translation unit is compiled with -fmad=false (exact mode).  dpcu_cull_fma.cu includes
 // it again with DPCU_FMA_VARIANT defined and -fmad=true to provide the reporting-only fast mode.
@@ -29,18 +29,15 @@
 namespace dpcu
 {
   constexpr int      kCullThreads    = 256;                 // objects per tile = threads per CTA
-  constexpr int      kWordsPerTile   = kCullThreads / 32;
   constexpr uint32_t kSegObjectsLog2 = 13;                  // 8192 objects = 256 words per segment
   constexpr uint32_t kSegWords       = 1u << ( kSegObjectsLog2 - 5 );
-  constexpr uint32_t kSuperSegsLog2  = 7;                   // 128 segments = 1 Mi objects per super-segment
-  constexpr int      kMaxPeers       = 8;
+    constexpr int      kMaxPeers       = 8;
 
   struct ViewOut
   {
     uint32_t *bits;      // in: previous visibility, out: new visibility
     uint32_t *chg;       // out: bits that flipped
-    uint32_t *seg;       // += popc per 8192-object segment
-    uint32_t *super;     // += popc per 1 Mi-object super-segment
+    uint32_t *seg;       // += popc per 8192-object segment; turned into an exclusive prefix by the last CTA
     uint32_t *peer[kMaxPeers];   // optional: full bitsets on peer GPUs (NVLink stores)
   };
 
@@ -55,6 +52,8 @@ namespace dpcu
     uint32_t      nPeers;
     uint32_t      peerWordOffset;
     int           buildChanged;
+    uint32_t      nSegs;
+    uint32_t     *done;      // CTA completion ticket (last CTA scans the segment counters)
     ViewOut       out[NV];
     float4        vp[NV][4];
   };
@@ -64,6 +63,53 @@ namespace dpcu
 #else
 #define DPCU_KERNEL_NAME( name ) name##_fma
 #endif
+
+  // The CTA that finishes last turns every view's per-segment changed counts into an exclusive
+  // prefix (seg[s] = number of changed objects before segment s, seg[nSegs] = total), in place.
+  // Replaces the XOR + traverseBits bookkeeping of ResultBitSet::updateChanged
+  // (dp/culling/src/ResultBitSet.cpp:100-107) together with the compaction kernel below.
+  template <int NV>
+  __device__ __forceinline__ void scanSegmentsInLastCta( ViewOut const ( &out )[NV], uint32_t nSegs, uint32_t *done )
+  {
+    __shared__ uint32_t sLast;
+    __shared__ uint32_t sPart[kCullThreads / 32];
+    __threadfence();                       // this CTA's counter updates are visible before its ticket
+    __syncthreads();
+    if ( threadIdx.x == 0 ) sLast = ( atomicAdd( done, 1u ) == gridDim.x - 1 ) ? 1u : 0u;
+    __syncthreads();
+    if ( !sLast ) return;
+    __threadfence();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t total = nSegs + 1;                              // the extra entry receives the grand total
+    const uint32_t chunk = ( total + kCullThreads - 1 ) / kCullThreads;
+    const uint32_t b = threadIdx.x * chunk, e = min( b + chunk, total );
+#pragma unroll 1
+    for ( int v = 0; v < NV; ++v )
+    {
+      uint32_t *seg = out[v].seg;
+      uint32_t sum = 0;
+      for ( uint32_t k = b; k < e; ++k ) sum += __ldcg( seg + k );
+      uint32_t incl = sum;
+#pragma unroll
+      for ( int d = 1; d < 32; d <<= 1 )
+      {
+        uint32_t t = __shfl_up_sync( 0xffffffffu, incl, d );
+        if ( lane >= d ) incl += t;
+      }
+      if ( lane == 31 ) sPart[warp] = incl;
+      __syncthreads();
+      uint32_t run = incl - sum;
+      for ( uint32_t w = 0; w < warp; ++w ) run += sPart[w];
+      for ( uint32_t k = b; k < e; ++k )
+      {
+        const uint32_t c = __ldcg( seg + k );
+        seg[k] = run;
+        run += c;
+      }
+      __syncthreads();
+    }
+    if ( threadIdx.x == 0 ) *done = 0u;    // ready for the next cull
+  }
 
   // ------------------------------------------------------------------------------------------
   // K2, direct variant: one thread per object, six 16-byte loads, persistent grid-stride tiles.
@@ -125,28 +171,28 @@ namespace dpcu
             o.chg[word] = c;
             if ( c )
             {
-              const uint32_t pc = __popc( c );
-              atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), pc );
-              atomicAdd( o.super + ( word >> ( kSegObjectsLog2 - 5 + kSuperSegsLog2 ) ), pc );
+              // one counter per 8192 objects: concurrently running CTAs spread over ~40 addresses.
+              // (A second, coarser level of counters was measured to serialise in L2: +0.5 ms at 64 Mi objects.)
+              atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
             }
           }
         }
       }
     }
+    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
 
 #ifndef DPCU_FMA_VARIANT
   // ------------------------------------------------------------------------------------------
-  // Ordered changed list.  One CTA per 8192-object segment and view: the CTA's base offset is
-  // the sum of the counters of all earlier segments (two levels, so at most 255 + 127 reads),
-  // then a block scan over the popcounts of its 256 flipped-bit words places every index.
+  // Ordered changed list.  One CTA per 8192-object segment and view: seg[] already holds the
+  // exclusive prefix, so the CTA only block-scans the popcounts of its 256 flipped-bit words and
+  // expands them; ascending group index order falls out of the layout (BitArray::traverseBits
+  // order, dp/util/BitArray.h:127-136).
   struct CompactArgs
   {
     uint32_t const *chg[DPCU_MAX_VIEWS];
     uint32_t const *seg[DPCU_MAX_VIEWS];
-    uint32_t const *super[DPCU_MAX_VIEWS];
     uint32_t       *changed[DPCU_MAX_VIEWS];
-    uint32_t       *count[DPCU_MAX_VIEWS];
     uint32_t        nWords;
     uint32_t        nSegs;
   };
@@ -156,30 +202,12 @@ namespace dpcu
     const uint32_t v    = blockIdx.y;
     const uint32_t s    = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const bool     last = ( s == a.nSegs - 1 );
-    const uint32_t mine = a.seg[v][s];
-    if ( mine == 0 && !last ) return;
+    const uint32_t base0 = a.seg[v][s];
+    if ( a.seg[v][s + 1] == base0 ) return;          // nothing changed in this segment
 
-    __shared__ uint32_t sBase;
     __shared__ uint32_t sWarp[8];
-
-    if ( warp == 0 )
-    {
-      uint32_t sum = 0;
-      const uint32_t sup = s >> kSuperSegsLog2;
-      for ( uint32_t k = lane; k < sup; k += 32 ) sum += a.super[v][k];
-      for ( uint32_t k = ( sup << kSuperSegsLog2 ) + lane; k < s; k += 32 ) sum += a.seg[v][k];
-#pragma unroll
-      for ( int d = 16; d > 0; d >>= 1 ) sum += __shfl_xor_sync( 0xffffffffu, sum, d );
-      if ( lane == 0 )
-      {
-        sBase = sum;
-        if ( last ) *a.count[v] = sum + mine;
-      }
-    }
-
     const uint32_t w = s * kSegWords + threadIdx.x;
-    uint32_t c = ( mine && w < a.nWords ) ? a.chg[v][w] : 0u;
+    uint32_t c = ( w < a.nWords ) ? a.chg[v][w] : 0u;
     const uint32_t pc = __popc( c );
     uint32_t incl = pc;
 #pragma unroll
@@ -190,8 +218,7 @@ namespace dpcu
     }
     if ( lane == 31 ) sWarp[warp] = incl;
     __syncthreads();
-    if ( mine == 0 ) return;
-    uint32_t off = sBase + incl - pc;
+    uint32_t off = base0 + incl - pc;
     for ( uint32_t k = 0; k < warp; ++k ) off += sWarp[k];
     uint32_t *out = a.changed[v];
     const uint32_t base = w << 5;
@@ -370,7 +397,7 @@ namespace dpcu
 struct dpcuCullResult
 {
   dpcuCull *ctx = nullptr;
-  dpcu::DeviceArray bits, chg, changed, counters;   // counters: seg[] | super[] | count
+  dpcu::DeviceArray bits, chg, changed, counters;   // counters: done | seg[0..nSegs] (count = seg[nSegs])
   size_t   n = 0;                // object count the stored bits are valid for (ResultBitSet::m_results size)
   size_t   capWords = 0;
   size_t   nSegsCap = 0;
@@ -381,9 +408,10 @@ struct dpcuCullResult
   size_t   peerWordOffset = 0;
   dpcuCullResult *next = nullptr, *prev = nullptr;
 
-  uint32_t *segPtr() const { return static_cast<uint32_t *>( counters.ptr ); }
-  uint32_t *superPtr() const { return segPtr() + nSegsCap; }
-  uint32_t *countPtr() const { return superPtr() + ( nSegsCap >> dpcu::kSuperSegsLog2 ) + 1; }
+  size_t   nSegs = 0;            // segments of the last run; the changed count lives at seg[nSegs]
+  uint32_t *donePtr() const { return static_cast<uint32_t *>( counters.ptr ); }
+  uint32_t *segPtr() const { return static_cast<uint32_t *>( counters.ptr ) + 4; }
+  uint32_t *countPtr() const { return segPtr() + nSegs; }
 };
 
 struct dpcuCull
@@ -455,7 +483,7 @@ namespace dpcu
     {
       size_t cap = nSegs + 1 + nSegs / 2;
       cap = ( cap + 127 ) & ~size_t( 127 );
-      size_t entries = cap + ( cap >> kSuperSegsLog2 ) + 1 + 1;
+      size_t entries = cap + 8;
       DPCU_TRY( r->counters.reserve( entries * 4, false, stream ) );
       r->nSegsCap = cap;
       DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, r->counters.capacity, stream ) );
@@ -474,6 +502,8 @@ namespace dpcu
     args.n        = uint32_t( ctx->n );
     args.nTiles   = uint32_t( divUp( ctx->n, size_t( kCullThreads ) ) );
     args.buildChanged = ctx->optChanged;
+    args.nSegs    = uint32_t( divUp( ctx->n, size_t( 1 ) << kSegObjectsLog2 ) );
+    args.done     = results[0]->donePtr();
     args.nPeers   = 0;
     for ( int v = 0; v < NV; ++v )
     {
@@ -481,7 +511,6 @@ namespace dpcu
       args.out[v].bits  = static_cast<uint32_t *>( r->bits.ptr );
       args.out[v].chg   = static_cast<uint32_t *>( r->chg.ptr );
       args.out[v].seg   = r->segPtr();
-      args.out[v].super = r->superPtr();
       for ( int p = 0; p < kMaxPeers; ++p ) args.out[v].peer[p] = p < r->nPeers ? r->peer[p] : nullptr;
       if ( uint32_t( r->nPeers ) > args.nPeers ) args.nPeers = uint32_t( r->nPeers );
       args.peerWordOffset = uint32_t( r->peerWordOffset );
@@ -758,8 +787,9 @@ extern "C"
         ++ctx->launches;
         r->n = n;
       }
-      // zero seg[] | super[] | count (one contiguous block, a few KiB)
-      DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, ( r->nSegsCap + ( r->nSegsCap >> dpcu::kSuperSegsLog2 ) + 2 ) * 4, s ) );
+      // zero done | seg[0..nSegs] (one contiguous block, a few KiB)
+      r->nSegs = nSegs;
+      DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, ( nSegs + 1 + 4 ) * 4, s ) );
       r->ran = true;
     }
     if ( !n ) return DPCU_OK;
@@ -785,9 +815,7 @@ extern "C"
         dpcuCullResult *r = results[v];
         ca.chg[v] = static_cast<uint32_t const *>( r->chg.ptr );
         ca.seg[v] = r->segPtr();
-        ca.super[v] = r->superPtr();
         ca.changed[v] = static_cast<uint32_t *>( r->changed.ptr );
-        ca.count[v] = r->countPtr();
       }
       ca.nWords = uint32_t( dpcu::divUp( n, 32 ) );
       ca.nSegs = uint32_t( nSegs );
