@@ -1,0 +1,499 @@
+#!/usr/bin/env python
+"""bench.py - culled objects/s of the B200 culling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic input: a frustum cull of the
+whole resident scene against a new camera, producing the visibility bitset and the ordered
+changed-object list.  Under torchrun (N > 1) every rank owns a contiguous slice of the object
+array on its own GPU (weak scaling: the slice size per GPU is fixed), there is no data-path
+collective, and rank 0 prints ONE JSON line; `value` is the whole-job objects/s.
+
+Workloads:
+    c4-single   (default) 64 Mi random objects per GPU, one matrix each, single frustum - the
+                configuration BASELINE.json's target is quoted on ("64M-object cull at 1 GPU").
+    c2          1 Mi objects (fits in L2: an L2-flushing write runs between timed steps)
+    c4          64 Mi objects x 6 cube-map frusta in one pass
+    c3          16 Mi objects under a 4-level, 17.9 M-node transform hierarchy, every local
+                matrix dirty every step: propagate (K1) + cull (K2) straight out of the tree
+    c5          256 Mi objects strong-scaled over the N GPUs
+
+Inputs are resident in HBM when the timed region starts (`value`); `e2e` is the same metric
+through the C ABI with HOST buffers: per step the camera goes in and the bitset + changed list
+come back into pinned host memory (host<->device copies inside the timed region).
+`--impl reference` times the reference's own CPU culler (oracle/_ref, the unmodified
+dp::culling::cpu::Manager) on the box's host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "culled objects/sec"
+UNIT = "objects/s"
+
+WORKLOADS = {
+    #  name        objects/GPU  views  seed          scaling
+    "c4-single": (1 << 26, 1, 0x5EED0004, "weak"),
+    "c2":        (1 << 20, 1, 0x5EED0002, "weak"),
+    "c4":        (1 << 26, 6, 0x5EED0004, "weak"),
+    "c3":        (1 << 24, 1, 0x5EED0003, "weak"),
+    "c5":        (1 << 28, 1, 0x5EED0005, "strong"),
+}
+C3_LEVELS = (4096, 65536, 1048576, 16777216)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load.  The sampler is
+    started before the warm-up (nvidia-smi needs a few hundred ms to deliver its first line) and
+    every line is stamped on arrival; the summary prefers the samples that fell inside the timed
+    region and falls back to the whole loaded window (warm-up .. e2e) when the timed region was
+    shorter than the sampling period - `window` says which."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+        self.marks = {}
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.01)
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line))
+
+    def mark(self, name):
+        self.marks[name] = time.perf_counter()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+
+        def parse(lo, hi):
+            sm, mx, reasons, power = [], [], set(), []
+            for t, line in self.lines:
+                if not (lo <= t <= hi):
+                    continue
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])), mx.append(float(f[2])), power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons, power
+
+        m = self.marks
+        window = "timed"
+        sm, mx, reasons, power = parse(m.get("timed0", 0), m.get("timed1", 1e300))
+        if len(sm) < 2:
+            window = "load (warm-up..e2e; timed region shorter than the sampling period)"
+            sm, mx, reasons, power = parse(m.get("load0", 0), m.get("load1", 1e300))
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class CpuCuller:
+    """The reference CPU culler on a slice of the workload: oracle/_ref (kind "reference") when
+    the compiled reference is present, else the C restatement (kind "port")."""
+
+    def __init__(self, seed, first, count, threads):
+        from oracle import loader
+        from pipeline_b200 import scenes
+        self.threads = threads
+        self.count = count
+        per = count // threads
+        self.slices = []
+        self.kind = "reference" if loader.Reference.available() else "port"
+        ref = loader.Reference() if self.kind == "reference" else None
+        port = loader.Port()
+        self.port = port
+
+        def setup(t):
+            lower4, extent4, upper4, mats, tidx = scenes.random_objects(seed, first + t * per, per)
+            tidx = np.arange(per, dtype=np.uint32)
+            if ref is not None:
+                s = ref.cull(0)
+                s.add_objects(np.ascontiguousarray(lower4[:, :3]), np.ascontiguousarray(upper4[:, :3]), tidx)
+                s.set_matrices(mats.reshape(-1))
+                r = s.result_create()
+                return (s, r, mats)
+            return (lower4, extent4, tidx, mats.reshape(-1))
+
+        ts, out = [], [None] * threads
+
+        def work(t):
+            out[t] = setup(t)
+        for t in range(threads):
+            th = threading.Thread(target=work, args=(t,))
+            th.start()
+            ts.append(th)
+        for th in ts:
+            th.join()
+        self.slices = out
+        self.total = per * threads
+
+    def step(self, vp):
+        """One cull of every slice, all threads concurrently; returns wall seconds."""
+        def work(t):
+            sl = self.slices[t]
+            if self.kind == "reference":
+                sl[0].cull(sl[1], vp)
+            else:
+                self.port.cull_bits(sl[0], sl[1], sl[2], sl[3], vp)
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(self.threads)]
+        t0 = time.perf_counter()
+        for th in ts:
+            th.start()
+        for th in ts:
+            th.join()
+        return time.perf_counter() - t0
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from pipeline_b200 import scenes
+    n_per, views, seed, scaling = WORKLOADS[args.workload]
+    cores = host_cores()
+    threads = max(1, min(cores, 128))
+    per_thread = 1 << 19
+    culler = CpuCuller(seed, 0, per_thread * threads, threads)
+    cams = [scenes.orbit_camera(f) for f in range(args.warmup + args.steps)]
+    for f in range(args.warmup):
+        culler.step(cams[f])
+    secs = [culler.step(cams[args.warmup + f]) for f in range(args.steps)]
+    ms = 1000.0 * sum(secs) / len(secs)
+    value = culler.total / (ms / 1000.0)
+    sample = ("%d objects (%d threads x %d, first objects of the %s scene, seed 0x%X), steady-state cull() per step, "
+              "one %s per thread" % (culler.total, threads, per_thread, args.workload, seed,
+                                     "dp::culling::cpu::Manager" if culler.kind == "reference" else "C port loop"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "objects_per_step": culler.total, "views": 1,
+                   "note": "reference CPU culler on host cores; a step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": culler.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_single_core(workload, seed):
+    """The reference as shipped is single-threaded (the omp pragma is commented out,
+    dp/culling/cpu/src/ManagerImpl.cpp:510): 1 core, bounded sample, steady state."""
+    from pipeline_b200 import scenes
+    n = 1 << 22
+    t0 = time.perf_counter()
+    culler = CpuCuller(seed, 0, n, 1)
+    setup_s = time.perf_counter() - t0
+    cams = [scenes.orbit_camera(f) for f in range(12)]
+    first = culler.step(cams[0])               # includes GroupCPU::updateOBBs
+    culler.step(cams[1])
+    secs = [culler.step(cams[2 + f]) for f in range(10)]
+    med = float(np.median(secs))
+    return {"value": n / med, "unit": UNIT, "cores": 1, "kind": culler.kind,
+            "sample": "first %d objects of the %s scene (seed 0x%X), median of 10 steady-state cull() calls; "
+                      "first cull incl. OBB build %.1f M objects/s; setup %.1f s" % (n, workload, seed, n / first / 1e6, setup_s)}
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from pipeline_b200 import capi, scenes
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    capi.device_select(device)
+    torch.cuda.set_device(device)
+
+    n_per, views, seed, scaling = WORKLOADS[args.workload]
+    if scaling == "strong":
+        n_per = n_per // world
+    n_total = n_per * world
+    first = rank * n_per
+    W, K = args.warmup, args.steps
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        capi.device_sync()
+
+    # ---------------- scene, resident in HBM
+    stream = capi.Stream()
+    tree = None
+    if args.workload == "c3":
+        entries, offsets, n_nodes = scenes.hierarchy_topology(C3_LEVELS)
+        tree = capi.Tree(device)
+        tree.set_topology(entries, offsets, n_nodes)
+        del entries
+        first_leaf = n_nodes - n_per
+        lo, ex = capi.Buffer(n_per * 16), capi.Buffer(n_per * 16)
+        scratch = capi.Buffer(n_per * 64)
+        # objects: random boxes; object i is bound to leaf i (transformIndex = first_leaf + i)
+        capi.scene_generate(seed, 0, n_per, (-first_leaf) & 0xFFFFFFFF, lo.ptr, ex.ptr, scratch.ptr)
+        capi.device_sync()
+        scratch.close()
+        # local matrices of every node: rigid transforms from the same generator (bench input only)
+        lptr, _ = tree.local_ptr()
+        lo2, ex2 = capi.Buffer(n_nodes * 16), capi.Buffer(n_nodes * 16)
+        capi.scene_generate(seed + 1, 0, n_nodes, 0, lo2.ptr, ex2.ptr, lptr)
+        capi.device_sync()
+        lo2.close(), ex2.close()
+        mats = None
+    else:
+        lo, ex, mats = capi.Buffer(n_per * 16), capi.Buffer(n_per * 16), capi.Buffer(n_per * 64)
+        capi.scene_generate(seed, first, n_per, first, lo.ptr, ex.ptr, mats.ptr)
+    capi.device_sync()
+
+    ctx = capi.Cull(device)
+    ctx.set_objects(lo.ptr, ex.ptr, None, capi.MEM_DEVICE, n=n_per)
+    if tree is not None:
+        wptr, cnt = tree.world_ptr()
+        ctx.bind_matrices(wptr, cnt)
+    else:
+        ctx.bind_matrices(mats.ptr, n_per)
+    ctx.set_option(capi.OPT_PROFILE, 1)
+    results = [ctx.result_create() for _ in range(views)]
+
+    if views > 1:
+        # six static faces plus a slowly translating eye so that the changed lists are not empty
+        cams = []
+        for f in range(W + 2 * K + 4):
+            eye = (3.0 * f, 0.0, 0.0)
+            cams.append(np.ascontiguousarray(scenes.cube_map_cameras(eye)[:views], np.float32))
+    else:
+        cams = [np.ascontiguousarray(scenes.orbit_camera(f), np.float32).reshape(1, 16) for f in range(W + 2 * K + 4)]
+
+    flush = None
+    if n_per * 96 < 200e6:                     # working set fits in the 126 MB L2: flush between timed steps
+        flush = capi.Buffer(256 << 20)
+
+    def step(f, s=stream):
+        if tree is not None:
+            tree.mark_dirty(1, tree.n_nodes - 1)   # every local matrix "rewritten" this frame
+            tree.compute(s)
+        ctx.run(results, cams[f], s)
+
+    sampler = ClockSampler(device)
+    sampler.start()
+    sampler.mark("load0")
+    for f in range(W):
+        step(f)
+    stream.sync()
+    ctx.kernel_time()
+    launches0 = ctx.launches() + (tree.launches() if tree else 0)
+
+    # ---------------- timed region: K steps, device-resident inputs
+    e0, e1 = capi.Event(), capi.Event()
+    barrier()
+    sampler.mark("timed0")
+    if flush is None:
+        e0.record(stream)
+        for f in range(K):
+            step(W + f)
+        e1.record(stream)
+        stream.sync()
+        ms_total = e0.elapsed_ms(e1)
+    else:
+        ms_total = 0.0
+        for f in range(K):
+            flush.fill(f & 0xFF)               # > L2 bytes written between timed iterations
+            capi.device_sync()
+            e0.record(stream)
+            step(W + f)
+            e1.record(stream)
+            stream.sync()
+            ms_total += e0.elapsed_ms(e1)
+    barrier()
+    sampler.mark("timed1")
+    launches1 = ctx.launches() + (tree.launches() if tree else 0)
+    k_ms, k_n = ctx.kernel_time()
+    changed = [r.changed_count() for r in results]
+
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = n_total / (ms_per_step / 1000.0)
+
+    # ---------------- e2e: same steps through the C ABI with host buffers
+    n_words = (n_per + 31) // 32
+    pinned_bits = [capi.HostBuffer(n_words * 4) for _ in range(views)]
+    pinned_chg = [capi.HostBuffer(max(n_per, 1) * 4) for _ in range(views)]
+    hb = [p.array(np.uint32) for p in pinned_bits]
+    hc = [p.array(np.uint32) for p in pinned_chg]
+    pinned_vp = capi.HostBuffer(views * 64)
+    hvp = pinned_vp.array(np.float32)
+    import ctypes as C
+    L = capi.lib()
+    u32p = C.POINTER(C.c_uint32)
+
+    def e2e_step(f):
+        hvp[:] = cams[f].reshape(-1)           # the step's input lives in pinned host memory
+        if tree is not None:
+            tree.mark_dirty(1, tree.n_nodes - 1)
+            tree.compute(stream)
+        ctx.run(results, hvp, stream)
+        d2h = 0
+        for v in range(views):
+            capi.check(L.dpcuCullResultGetBits(results[v].h, hb[v].ctypes.data_as(u32p), n_words))
+            cnt = C.c_size_t()
+            capi.check(L.dpcuCullResultGetChanged(results[v].h, hc[v].ctypes.data_as(u32p), n_per, C.byref(cnt)))
+            d2h += n_words * 4 + 4 + cnt.value * 4
+        return d2h
+
+    for f in range(2):
+        e2e_step(W + K + f)
+    barrier()
+    d2h_bytes = 0
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for f in range(K):
+        d2h_bytes += e2e_step(W + K + 2 + f)
+    e1.record(stream)
+    stream.sync()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    e2e_ms = max(e0.elapsed_ms(e1), wall_ms)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = n_total / (e2e_ms / K / 1000.0)
+    ctx.kernel_time()
+    sampler.mark("load1")
+    clocks = sampler.stop()
+
+    # ---------------- roofline of the dominant kernel (K2, the cull kernel)
+    peak, peak_src = measured_peak()
+    alg_bytes = n_per * (96.0 + 0.25 * views)            # per launch, per GPU
+    k_avg_ms = k_ms / max(k_n, 1)
+    achieved = alg_bytes / (k_avg_ms / 1000.0) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_cull_kernel_summary.json")))
+        for p in prof.get("captures", []):
+            if p.get("workload") == args.workload and p.get("objects") == n_per and p.get("views") == views:
+                traffic = p["dram_bytes_read"] + p["dram_bytes_write"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "cullDirectKernel<%d>" % views, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n),
+                "step_share": k_ms / ms_total if ms_total else None}
+    if tree is not None:
+        nodes = sum(C3_LEVELS)
+        alg_tree = nodes * 136.0 + (1 + sum(C3_LEVELS[:-1])) * 64.0
+        roofline["step_algorithmic_bytes"] = alg_tree + alg_bytes
+        roofline["step_achieved"] = (alg_tree + alg_bytes) / (ms_per_step / 1000.0) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "objects_per_gpu": n_per, "objects_total": n_total, "views": views,
+                   "matrices": "one per object (transformIndex = i)" if tree is None else "4-level tree, %d nodes" % tree.n_nodes,
+                   "camera": "new view-projection every step", "changed_per_step_last": changed,
+                   "l2": "inputs (%.1f GB per GPU) larger than L2" % (n_per * 96 / 1e9) if flush is None
+                         else "256 MiB flush write between timed steps",
+                   "parallelism": "object slices, one per GPU, no data-path collective" if world > 1 else "single GPU",
+                   "exact_mode": "-fmad=false, bit-exact vs dp::culling::cpu"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": views * 64, "d2h_bytes_per_step": d2h_bytes // K,
+                "ms_per_step": e2e_ms / K,
+                "what": "camera from pinned host memory in, visibility bitset + changed list into pinned host memory out, "
+                        "through dpcuCullRun / dpcuCullResultGetBits / dpcuCullResultGetChanged"},
+        "gpu_launches": int(launches1 - launches0),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single_core(args.workload, seed)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for r in results:
+        r.close()
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4-single", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

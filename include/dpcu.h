@@ -190,8 +190,13 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 #define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */
+#define DPCU_CULL_OPT_PROFILE       5   /* 1 = bracket every cull-kernel launch with CUDA events (see below) */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
+/* With DPCU_CULL_OPT_PROFILE = 1: device time spent in the cull kernel (K2 only, not the memset /
+ * compaction around it) since the last call, measured with CUDA events on the launching stream;
+ * synchronises those events and resets the accumulator.  This is the number bench.py's roofline uses. */
+int dpcuCullGetKernelTime(dpcuCull *ctx, double *totalMs, uint64_t *launches);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int dpcuCullGetLaunchCount(const dpcuCull *ctx, uint64_t *launches);
 

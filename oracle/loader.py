@@ -138,7 +138,7 @@ class RefCull:
         self.lib = lib
         self.h = lib.dpref_cull_create(backend)
         if not self.h:
-            raise RuntimeError("dpref_cull_create(%d) failed" % backend)
+            raise RuntimeError("dpref_cull_create(%d) failed: %s" % (backend, lib.dpref_create_error().decode()))
         self._keep = None
 
     def close(self):
@@ -220,6 +220,17 @@ class RefCull:
         self._chk(self.lib.dpref_cull_bounding_box(self.h, _fp(out)))
         return out
 
+    # extensions of dp::culling::cuda::Manager (only in the drop-in test library)
+    def set_device_matrices(self, device_ptr, count):
+        self.lib.dpref_cull_set_device_matrices.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        self._chk(self.lib.dpref_cull_set_device_matrices(self.h, device_ptr, count))
+
+    def cull_multi(self, results, vps):
+        vps = np.ascontiguousarray(vps, dtype=np.float32).reshape(-1)
+        arr = (C.c_int * len(results))(*results)
+        self.lib.dpref_cull_run_multi.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, _f32p]
+        self._chk(self.lib.dpref_cull_run_multi(self.h, arr, len(results), _fp(vps)))
+
 
 class RefTree:
     """One reference ``dp::transform::Tree``."""
@@ -292,6 +303,7 @@ def _declare_ref(lib):
     lib.dpref_cull_create.argtypes = [C.c_int]
     lib.dpref_cull_create.restype = C.c_void_p
     lib.dpref_cull_destroy.argtypes = [C.c_void_p]
+    lib.dpref_create_error.restype = C.c_char_p
     lib.dpref_last_error.argtypes = [C.c_void_p]
     lib.dpref_last_error.restype = C.c_char_p
     lib.dpref_cull_add_objects.argtypes = [C.c_void_p, C.c_size_t, _f32p, _f32p, _u32p]

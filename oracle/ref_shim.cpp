@@ -30,11 +30,9 @@
 #include <string>
 #include <vector>
 
-#ifndef DPREF_WITH_CUDA
 // dp/culling/src/Manager.cpp is not compiled (it pulls in the OpenGL backend,
 // Manager.cpp:44-45); the only symbol it owns on this path is the empty destructor.
 dp::culling::Manager::~Manager() {}
-#endif
 
 namespace
 {
@@ -88,6 +86,8 @@ namespace
   }
 }
 
+static std::string g_createError;
+
 #define SESSION( p ) ( static_cast<Session *>( p ) )
 #define TREE( p )    ( static_cast<TreeSession *>( p ) )
 
@@ -115,11 +115,14 @@ extern "C"
       s->group = s->manager->groupCreate();
       return s.release();
     }
-    catch ( std::exception const & )
+    catch ( std::exception const & e )
     {
+      g_createError = e.what();
       return nullptr;
     }
   }
+
+  char const * dpref_create_error() { return g_createError.c_str(); }
 
   void dpref_cull_destroy( void * p )
   {
@@ -295,6 +298,42 @@ extern "C"
     }
     catch ( std::exception const & e ) { s->error = e.what(); return 1; }
   }
+
+#ifdef DPREF_WITH_CUDA
+  // ---------------------------------------------------------------- cuda-only extensions of the new backend
+  int dpref_cull_set_device_matrices( void * p, void const * deviceMatrices, size_t count )
+  {
+    Session * s = SESSION( p );
+    try
+    {
+      dp::culling::cuda::Manager * m = dynamic_cast<dp::culling::cuda::Manager *>( s->manager.get() );
+      if ( !m ) { s->error = "not a cuda manager"; return 1; }
+      m->groupSetDeviceMatrices( s->group, deviceMatrices, count );
+      return 0;
+    }
+    catch ( std::exception const & e ) { s->error = e.what(); return 1; }
+  }
+
+  int dpref_cull_run_multi( void * p, int const * results, int nViews, float const * viewProjections16 )
+  {
+    Session * s = SESSION( p );
+    try
+    {
+      dp::culling::cuda::Manager * m = dynamic_cast<dp::culling::cuda::Manager *>( s->manager.get() );
+      if ( !m ) { s->error = "not a cuda manager"; return 1; }
+      std::vector<dp::culling::ResultSharedPtr> r;
+      std::vector<dp::math::Mat44f> vp;
+      for ( int v = 0; v < nViews; ++v )
+      {
+        r.push_back( s->results[results[v]] );
+        vp.push_back( toMat( viewProjections16 + 16 * v ) );
+      }
+      m->cullMultiView( s->group, r, vp );
+      return 0;
+    }
+    catch ( std::exception const & e ) { s->error = e.what(); return 1; }
+  }
+#endif
 
   // ---------------------------------------------------------------- dp::transform::Tree
   void * dpref_tree_create() { return new TreeSession; }

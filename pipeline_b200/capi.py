@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM = 1, 2, 3, 4
+OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE = 1, 2, 3, 4, 5
 MAX_VIEWS = 8
 
 _vp = C.c_void_p
@@ -103,6 +103,7 @@ def _declare(L):
         "dpcuCullSetOption": [_vp, C.c_int, C.c_int],
         "dpcuCullGetOption": [_vp, C.c_int, C.POINTER(C.c_int)],
         "dpcuCullGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
+        "dpcuCullGetKernelTime": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
         "dpcuCullResultSetPeerBits": [_vp, C.POINTER(_vp), C.c_int, C.c_size_t],
         "dpcuIpcGetHandle": [_vp, C.c_char_p],
         "dpcuIpcOpen": [C.c_char_p, C.POINTER(_vp)],
@@ -419,6 +420,12 @@ class Cull:
         v = C.c_uint64()
         check(lib().dpcuCullGetLaunchCount(self.h, C.byref(v)))
         return v.value
+
+    def kernel_time(self):
+        """(total ms, launches) of the cull kernel since the last call; needs OPT_PROFILE = 1."""
+        ms, n = C.c_double(), C.c_uint64()
+        check(lib().dpcuCullGetKernelTime(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def close(self):
         if self.h:

@@ -25,6 +25,7 @@
 #include "dpcu_internal.h"
 
 #include <new>
+#include <vector>
 
 namespace dpcu
 {
@@ -425,8 +426,10 @@ struct dpcuCull
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0;
   uint64_t     launches = 0;
+  std::vector<cudaEvent_t> profEvents;   // start/stop pairs of profiled cull-kernel launches
+  size_t       profUsed = 0;
   dpcuCullResult *results = nullptr;
 
   float4 const *matsPtr() const { return boundMats ? reinterpret_cast<float4 const *>( boundMats ) : static_cast<float4 const *>( mats.ptr ); }
@@ -525,6 +528,20 @@ namespace dpcu
     }
     int grid = ctx->smCount * perSm;
     if ( uint32_t( grid ) > args.nTiles ) grid = int( args.nTiles );
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    if ( ctx->optProfile )
+    {
+      while ( ctx->profEvents.size() < ctx->profUsed + 2 )
+      {
+        cudaEvent_t e;
+        DPCU_CUDA( cudaEventCreate( &e ) );
+        ctx->profEvents.push_back( e );
+      }
+      evStart = ctx->profEvents[ctx->profUsed];
+      evStop  = ctx->profEvents[ctx->profUsed + 1];
+      ctx->profUsed += 2;
+      DPCU_CUDA( cudaEventRecord( evStart, stream ) );
+    }
     if ( ctx->optFma )
     {
       DPCU_CUDA( launchCullDirectFma<NV>( args, grid, stream ) );
@@ -534,6 +551,7 @@ namespace dpcu
       cullDirectKernel<NV><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
     }
+    if ( evStop ) DPCU_CUDA( cudaEventRecord( evStop, stream ) );
     ++ctx->launches;
     return DPCU_OK;
   }
@@ -572,6 +590,7 @@ extern "C"
     cudaStreamSynchronize( ctx->stream );
     ctx->lowerIdx.release(); ctx->extent.release(); ctx->mats.release(); ctx->scratch.release(); ctx->maxIndex.release();
     ctx->staging.release();
+    for ( cudaEvent_t e : ctx->profEvents ) cudaEventDestroy( e );
     cudaStreamDestroy( ctx->stream );
     delete ctx;
     return DPCU_OK;
@@ -973,6 +992,7 @@ extern "C"
       case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;
+      case DPCU_CULL_OPT_PROFILE:      ctx->optProfile = value ? 1 : 0; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -987,8 +1007,27 @@ extern "C"
       case DPCU_CULL_OPT_FMA:          *value = ctx->optFma; break;
       case DPCU_CULL_OPT_CHANGED_LIST: *value = ctx->optChanged; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  *value = ctx->optCtasPerSm; break;
+      case DPCU_CULL_OPT_PROFILE:      *value = ctx->optProfile; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
+    return DPCU_OK;
+  }
+
+  int dpcuCullGetKernelTime( dpcuCull *ctx, double *totalMs, uint64_t *launches )
+  {
+    DPCU_REQUIRE( ctx && totalMs && launches, "NULL argument" );
+    dpcu::DeviceGuard guard( ctx->device );
+    double sum = 0.0;
+    for ( size_t i = 0; i + 1 < ctx->profUsed; i += 2 )
+    {
+      DPCU_CUDA( cudaEventSynchronize( ctx->profEvents[i + 1] ) );
+      float ms = 0.f;
+      DPCU_CUDA( cudaEventElapsedTime( &ms, ctx->profEvents[i], ctx->profEvents[i + 1] ) );
+      sum += ms;
+    }
+    *totalMs = sum;
+    *launches = ctx->profUsed / 2;
+    ctx->profUsed = 0;
     return DPCU_OK;
   }
 

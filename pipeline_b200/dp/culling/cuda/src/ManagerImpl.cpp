@@ -1,0 +1,367 @@
+// dp::culling::cuda - host side of the B200 culling backend.
+//
+// Derives ManagerBitSet exactly like the cpu and opengl backends do (they override objectCreate,
+// groupCreate, groupCreateResult and cull: dp/culling/cpu/inc/ManagerImpl.h:67-77,
+// dp/culling/opengl/inc/ManagerImpl.h:41-61) and keeps the group / object bookkeeping of
+// GroupBitSet / ObjectBitSet.  The result type is its own (ResultCUDA) because the changed list
+// and the bitset are produced on the GPU; resultGetChanged / resultObjectIsVisible are overridden
+// accordingly.  Every GPU operation goes through the C ABI of include/dpcu.h; a failing call is
+// rethrown as std::runtime_error like CUDA_VERIFY does (dp/cuda/Config.h:47-57).
+#include <dp/culling/cuda/inc/ManagerImpl.h>
+#include <dp/util/FrameProfiler.h>
+
+#include <cstring>
+#include <stdexcept>
+
+namespace dp
+{
+  namespace culling
+  {
+    namespace cuda
+    {
+      namespace
+      {
+        inline void verify( int status, char const * call )
+        {
+          if ( status != DPCU_OK )
+          {
+            throw std::runtime_error( std::string( call ) + ": " + dpcuGetLastError() );
+          }
+        }
+#define DPCU_VERIFY( call ) verify( call, #call )
+      }
+
+      /************************************************************************/
+      /* GroupCUDA                                                            */
+      /************************************************************************/
+      GroupCUDASharedPtr GroupCUDA::create( int device )
+      {
+        return( std::shared_ptr<GroupCUDA>( new GroupCUDA( device ) ) );
+      }
+
+      GroupCUDA::GroupCUDA( int device )
+        : m_ctx( nullptr )
+        , m_deviceMatrices( nullptr )
+        , m_deviceMatricesCount( 0 )
+        , m_deviceMatricesBound( false )
+      {
+        DPCU_VERIFY( dpcuCullCreate( &m_ctx, device ) );
+      }
+
+      GroupCUDA::~GroupCUDA()
+      {
+        dpcuCullDestroy( m_ctx );
+      }
+
+      void GroupCUDA::setDeviceMatrices( void const * deviceMatrices, size_t count )
+      {
+        m_deviceMatrices = deviceMatrices;
+        m_deviceMatricesCount = count;
+        m_deviceMatricesBound = false;
+        setBoundingBoxDirty( true );
+      }
+
+      void GroupCUDA::markObjectEdited( size_t groupIndex )
+      {
+        m_editedObjects.push_back( static_cast<uint32_t>( groupIndex ) );
+        setBoundingBoxDirty( true );
+      }
+
+      void GroupCUDA::update()
+      {
+        // ---- objects: whole array after add / remove (GroupBitSet.cpp:76-119 set m_inputChanged) ...
+        if ( m_inputChanged )
+        {
+          dp::util::ProfileEntry p( "cull::updateInputBuffer" );
+          size_t const n = getObjectCount();
+          m_stageLower.resize( 4 * n );
+          m_stageExtent.resize( 4 * n );
+          m_stageIndex.resize( n );
+          for ( size_t index = 0; index < n; ++index )
+          {
+            ObjectBitSetSharedPtr const & object = getObject( index );
+            memcpy( &m_stageLower[4 * index], object->getLowerLeft().getPtr(), 4 * sizeof(float) );
+            memcpy( &m_stageExtent[4 * index], object->getExtent().getPtr(), 4 * sizeof(float) );
+            m_stageIndex[index] = static_cast<uint32_t>( object->getTransformIndex() );
+          }
+          DPCU_VERIFY( dpcuCullSetObjects( m_ctx, m_stageLower.data(), m_stageExtent.data(), m_stageIndex.data(), n, DPCU_MEM_HOST ) );
+          m_inputChanged = false;
+          m_editedObjects.clear();
+        }
+        // ---- ... or just the live objects that were edited (objectSetBoundingBox / objectSetTransformIndex)
+        else if ( !m_editedObjects.empty() )
+        {
+          for ( size_t i = 0; i < m_editedObjects.size(); ++i )
+          {
+            size_t const index = m_editedObjects[i];
+            if ( index < getObjectCount() )
+            {
+              ObjectBitSetSharedPtr const & object = getObject( index );
+              uint32_t transformIndex = static_cast<uint32_t>( object->getTransformIndex() );
+              DPCU_VERIFY( dpcuCullSetObjectRange( m_ctx, index, 1, object->getLowerLeft().getPtr(), object->getExtent().getPtr()
+                                                 , &transformIndex, DPCU_MEM_HOST ) );
+            }
+          }
+          m_editedObjects.clear();
+        }
+
+        // ---- matrices
+        dp::util::ProfileEntry p( "cull::updateMatrices" );
+        if ( m_deviceMatrices )
+        {
+          if ( !m_deviceMatricesBound )
+          {
+            DPCU_VERIFY( dpcuCullBindMatrices( m_ctx, m_deviceMatrices, m_deviceMatricesCount ) );
+            m_deviceMatricesBound = true;
+          }
+          m_matricesChanged = false;
+        }
+        else if ( m_matricesChanged )
+        {
+          // pointer, count or stride changed: take everything (GroupBitSet.cpp:121-135)
+          DPCU_VERIFY( dpcuCullSetMatrices( m_ctx, getMatrices(), getMatricesCount(), getMatricesStride(), DPCU_MEM_HOST ) );
+          m_matricesChanged = false;
+        }
+        else
+        {
+          // only the matrices flagged through groupMatrixChanged (GroupBitSet.h:140-150)
+          struct Collector
+          {
+            Collector( std::vector<uint32_t> & indices ) : m_indices( indices ) {}
+            void operator()( size_t index ) { m_indices.push_back( static_cast<uint32_t>( index ) ); }
+            std::vector<uint32_t> & m_indices;
+          };
+          m_stageIndex.clear();
+          Collector collector( m_stageIndex );
+          m_dirtyMatrices.traverseBits( collector );
+          if ( !m_stageIndex.empty() )
+          {
+            DPCU_VERIFY( dpcuCullUpdateMatrices( m_ctx, m_stageIndex.data(), m_stageIndex.size(), getMatrices(), getMatricesStride(), DPCU_MEM_HOST ) );
+          }
+        }
+        m_dirtyMatrices.clear();
+        m_obbDirty = false;   // there is no OBB cache on the device: OBBs are rebuilt from the matrices in every cull
+      }
+
+      /************************************************************************/
+      /* ResultCUDA                                                           */
+      /************************************************************************/
+      ResultCUDASharedPtr ResultCUDA::create( GroupCUDASharedPtr const & parentGroup )
+      {
+        return( std::shared_ptr<ResultCUDA>( new ResultCUDA( parentGroup ) ) );
+      }
+
+      ResultCUDA::ResultCUDA( GroupCUDASharedPtr const & parentGroup )
+        : m_groupParent( parentGroup )
+        , m_result( nullptr )
+        , m_size( 0 )
+      {
+        DP_ASSERT( m_groupParent );
+        DPCU_VERIFY( dpcuCullResultCreate( m_groupParent->getContext(), &m_result ) );
+        m_groupParent->attach( this );     // object index remap events, like ResultBitSet.cpp:41-49
+      }
+
+      ResultCUDA::~ResultCUDA()
+      {
+        m_groupParent->detach( this );
+        dpcuCullResultDestroy( m_result );
+      }
+
+      void ResultCUDA::fetch()
+      {
+        dp::util::ProfileEntry p( "ResultBitSet::updateChanged" );   // same profiler key as the host diff it replaces
+
+        size_t const count = m_groupParent->getObjectCount();
+        size_t changed = 0;
+        DPCU_VERIFY( dpcuCullResultGetChangedCount( m_result, &changed ) );
+        m_changedIndices.resize( changed );
+        if ( changed )
+        {
+          DPCU_VERIFY( dpcuCullResultGetChanged( m_result, m_changedIndices.data(), changed, &changed ) );
+        }
+        m_changedObjects.clear();
+        m_changedObjects.reserve( changed );
+        for ( size_t i = 0; i < changed; ++i )
+        {
+          m_changedObjects.push_back( m_groupParent->getObject( m_changedIndices[i] ) );   // ascending group index
+        }
+
+        m_size = count;
+        m_bits.resize( ( count + 31 ) / 32 );
+        if ( count )
+        {
+          DPCU_VERIFY( dpcuCullResultGetBits( m_result, m_bits.data(), m_bits.size() ) );
+        }
+      }
+
+      bool ResultCUDA::isVisible( ObjectBitSetSharedPtr const & object ) const
+      {
+        // ResultBitSet::isVisible, dp/culling/ResultBitSet.h:69-76
+        size_t groupIndex = object->getGroupIndex();
+        DP_ASSERT( groupIndex != ~0 );
+        return ( groupIndex < m_size ) ? !!( m_bits[groupIndex >> 5] & ( 1u << ( groupIndex & 31 ) ) ) : true;
+      }
+
+      void ResultCUDA::onNotify( dp::util::Event const & event, dp::util::Payload * /*payload*/ )
+      {
+        // ResultBitSet::onNotify, dp/culling/src/ResultBitSet.cpp:110-128 - on the device copy and on the host copy
+        GroupBitSet::Event const & groupEvent = static_cast<GroupBitSet::Event const &>( event );
+        size_t const newIndex = groupEvent.getNewIndex(), oldIndex = groupEvent.getOldIndex();
+        DPCU_VERIFY( dpcuCullResultMoveBit( m_result, oldIndex, newIndex ) );
+        if ( newIndex < m_size )
+        {
+          bool value = true;
+          if ( oldIndex < m_size )
+          {
+            value = !!( m_bits[oldIndex >> 5] & ( 1u << ( oldIndex & 31 ) ) );
+          }
+          if ( value ) m_bits[newIndex >> 5] |= 1u << ( newIndex & 31 );
+          else         m_bits[newIndex >> 5] &= ~( 1u << ( newIndex & 31 ) );
+        }
+      }
+
+      void ResultCUDA::onDestroyed( dp::util::Subject const & /*subject*/, dp::util::Payload * /*payload*/ )
+      {
+        // same contract as ResultBitSet::onDestroyed (ResultBitSet.cpp:130-133): the group must outlive its results
+        throw std::runtime_error( "The method or operation is not implemented." );
+      }
+
+      /************************************************************************/
+      /* ManagerImpl                                                          */
+      /************************************************************************/
+      Manager* Manager::create( int device )
+      {
+        return new ManagerImpl( device );
+      }
+
+      ManagerImpl::ManagerImpl( int device )
+        : m_device( device )
+      {
+        int count = 0;
+        DPCU_VERIFY( dpcuDeviceCount( &count ) );   // throws when there is no GPU: no silent CPU path
+        if ( device < 0 || device >= count )
+        {
+          throw std::runtime_error( "dp::culling::cuda::Manager: device index out of range" );
+        }
+      }
+
+      ManagerImpl::~ManagerImpl()
+      {
+      }
+
+      ObjectSharedPtr ManagerImpl::objectCreate( PayloadSharedPtr const & userData )
+      {
+        return ObjectBitSet::create( userData );
+      }
+
+      void ManagerImpl::groupAddObject( GroupSharedPtr const & group, ObjectSharedPtr const & object )
+      {
+        ManagerBitSet::groupAddObject( group, object );
+        // The reference never connects an object to its group (hard part 5); this
+        // backend does, so that edits of live objects reach the device mirror.
+        std::static_pointer_cast<ObjectBitSet>( object )->setGroup( std::static_pointer_cast<GroupBitSet>( group ) );
+      }
+
+      void ManagerImpl::objectSetBoundingBox( ObjectSharedPtr const & object, dp::math::Box3f const & boundingBox )
+      {
+        ManagerBitSet::objectSetBoundingBox( object, boundingBox );
+        ObjectBitSetSharedPtr objectImpl = std::static_pointer_cast<ObjectBitSet>( object );
+        if ( GroupBitSetSharedPtr group = objectImpl->getGroup() )
+        {
+          std::static_pointer_cast<GroupCUDA>( group )->markObjectEdited( objectImpl->getGroupIndex() );
+        }
+      }
+
+      void ManagerImpl::objectSetTransformIndex( ObjectSharedPtr const & object, size_t index )
+      {
+        ManagerBitSet::objectSetTransformIndex( object, index );
+        ObjectBitSetSharedPtr objectImpl = std::static_pointer_cast<ObjectBitSet>( object );
+        if ( GroupBitSetSharedPtr group = objectImpl->getGroup() )
+        {
+          std::static_pointer_cast<GroupCUDA>( group )->markObjectEdited( objectImpl->getGroupIndex() );
+        }
+      }
+
+      GroupSharedPtr ManagerImpl::groupCreate()
+      {
+        return GroupCUDA::create( m_device );
+      }
+
+      ResultSharedPtr ManagerImpl::groupCreateResult( GroupSharedPtr const & group )
+      {
+        return ResultCUDA::create( std::static_pointer_cast<GroupCUDA>( group ) );
+      }
+
+      void ManagerImpl::groupSetDeviceMatrices( GroupSharedPtr const & group, void const * deviceMatrices, size_t numberOfMatrices )
+      {
+        std::static_pointer_cast<GroupCUDA>( group )->setDeviceMatrices( deviceMatrices, numberOfMatrices );
+      }
+
+      std::vector<ObjectSharedPtr> const & ManagerImpl::resultGetChanged( ResultSharedPtr const & result )
+      {
+        return( std::static_pointer_cast<ResultCUDA>( result )->getChangedObjects() );
+      }
+
+      bool ManagerImpl::resultObjectIsVisible( ResultSharedPtr const & result, ObjectSharedPtr const & object )
+      {
+        return( std::static_pointer_cast<ResultCUDA>( result )->isVisible( std::static_pointer_cast<ObjectBitSet>( object ) ) );
+      }
+
+      void ManagerImpl::cull( GroupSharedPtr const & group, ResultSharedPtr const & result, dp::math::Mat44f const & viewProjection )
+      {
+        dp::util::ProfileEntry p( "cull" );
+
+        GroupCUDASharedPtr groupImpl = std::static_pointer_cast<GroupCUDA>( group );
+        ResultCUDASharedPtr resultImpl = std::static_pointer_cast<ResultCUDA>( result );
+        if ( resultImpl->getGroup() != groupImpl )
+        {
+          throw std::runtime_error( "result does not belong to this group" );
+        }
+
+        groupImpl->update();
+        dpcuCullResult * handle = resultImpl->getHandle();
+        DPCU_VERIFY( dpcuCullRun( groupImpl->getContext(), &handle, viewProjection.getPtr(), 1, nullptr ) );
+        resultImpl->fetch();   // synchronous like the reference: the result is valid when cull returns
+      }
+
+      void ManagerImpl::cullMultiView( GroupSharedPtr const & group, std::vector<ResultSharedPtr> const & results
+                                     , std::vector<dp::math::Mat44f> const & viewProjections )
+      {
+        dp::util::ProfileEntry p( "cull" );
+
+        if ( results.size() != viewProjections.size() || results.empty() || results.size() > DPCU_MAX_VIEWS )
+        {
+          throw std::runtime_error( "cullMultiView: need 1..8 results and as many view-projection matrices" );
+        }
+        GroupCUDASharedPtr groupImpl = std::static_pointer_cast<GroupCUDA>( group );
+        std::vector<dpcuCullResult *> handles( results.size() );
+        std::vector<float> matrices( 16 * results.size() );
+        for ( size_t v = 0; v < results.size(); ++v )
+        {
+          handles[v] = std::static_pointer_cast<ResultCUDA>( results[v] )->getHandle();
+          memcpy( &matrices[16 * v], viewProjections[v].getPtr(), 16 * sizeof(float) );
+        }
+        groupImpl->update();
+        DPCU_VERIFY( dpcuCullRun( groupImpl->getContext(), handles.data(), matrices.data(), static_cast<int>( results.size() ), nullptr ) );
+        for ( size_t v = 0; v < results.size(); ++v )
+        {
+          std::static_pointer_cast<ResultCUDA>( results[v] )->fetch();
+        }
+      }
+
+      dp::math::Box3f ManagerImpl::calculateBoundingBox( GroupSharedPtr const & group ) const
+      {
+        GroupCUDASharedPtr groupImpl = std::static_pointer_cast<GroupCUDA>( group );
+        groupImpl->update();
+        float box[6];
+        DPCU_VERIFY( dpcuCullGetBoundingBox( groupImpl->getContext(), box ) );
+        dp::math::Box3f result;
+        // the C ABI already applied the Box3f( lower, upper ) construction of ManagerBitSet.cpp:304
+        result.update( dp::math::Vec3f( box[0], box[1], box[2] ) );
+        result.update( dp::math::Vec3f( box[3], box[4], box[5] ) );
+        return result;
+      }
+
+    } // namespace cuda
+  } // namespace culling
+} // namespace dp

@@ -18,10 +18,15 @@ from oracle.loader import Port, Reference
 class RefEngine:
     kind = "reference"
 
-    def __init__(self, ref: Reference | None = None):
+    def __init__(self, ref: Reference | None = None, backend: int = 0):
         self.ref = ref or Reference()
-        self.s = self.ref.cull(0)
+        self.s = self.ref.cull(backend)
         self.r = self.s.result_create()
+        if backend:
+            self.kind = "dp::culling::cuda::Manager"
+
+    def set_object(self, index, lower4, upper4, tidx):
+        self.s.set_object(index, lower4[:3], upper4[:3], tidx)
 
     def add(self, lower4, upper4, tidx):
         self.s.add_objects(np.ascontiguousarray(lower4[:, :3]), np.ascontiguousarray(upper4[:, :3]), tidx)
