@@ -313,6 +313,27 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_option(capi.OPT_PROFILE, 1)
     results = [ctx.result_create() for _ in range(views)]
 
+    # ---------------- multi-GPU: the bitset all-gather is the cull kernel's epilogue (NVLink peer stores)
+    gather = "none"
+    full_bits, peer_ptrs = [], []
+    if world > 1 and args.gather == "fused":
+        from pipeline_b200 import sharding
+        try:
+            words_total = sharding.total_words(n_total)
+            for v in range(views):
+                fb = capi.Buffer(words_total * 4)
+                fb.fill(0)
+                full_bits.append(fb)
+                handles = sharding.exchange_ipc(dist, capi.ipc_get_handle(fb.ptr))
+                ptrs = [fb.ptr if r == rank else capi.ipc_open(handles[r]) for r in range(world)]
+                peer_ptrs.append(ptrs)
+                results[v].set_peer_bits(ptrs, sharding.word_offset(first))
+            gather = "fused: every rank's cull kernel stores its words into all %d full bitsets (cudaIpc peer pointers)" % world
+        except Exception as e:                      # noqa: BLE001 - report, do not hide
+            gather = "none (peer mapping failed: %s)" % e
+            for v in range(views):
+                results[v].set_peer_bits([], 0)
+
     if views > 1:
         # six static faces plus a slowly translating eye so that the changed lists are not empty
         cams = []
@@ -422,6 +443,18 @@ def run_ours(args, rank, world, local_rank):
     sampler.mark("load1")
     clocks = sampler.stop()
 
+    # ---------------- multi-GPU: check the fused all-gather against the library collective (untimed)
+    gather_ok = None
+    if full_bits:
+        from pipeline_b200 import sharding
+        barrier()
+        local = torch.from_numpy(results[0].bits().view(np.int32)).cuda()
+        parts = sharding.allgather_words(dist, local, n_words)
+        want = torch.cat(parts).cpu().numpy().view(np.uint32)
+        got = np.zeros(sharding.total_words(n_total), np.uint32)
+        full_bits[0].download(got)
+        gather_ok = bool(np.array_equal(got, want[:len(got)]))
+
     # ---------------- roofline of the dominant kernel (K2, the cull kernel)
     peak, peak_src = measured_peak()
     alg_bytes = n_per * (96.0 + 0.25 * views)            # per launch, per GPU
@@ -455,6 +488,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs (%.1f GB per GPU) larger than L2" % (n_per * 96 / 1e9) if flush is None
                          else "256 MiB flush write between timed steps",
                    "parallelism": "object slices, one per GPU, no data-path collective" if world > 1 else "single GPU",
+                   "bitset_allgather": gather, "bitset_allgather_verified": gather_ok,
                    "exact_mode": "-fmad=false, bit-exact vs dp::culling::cpu"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": views * 64, "d2h_bytes_per_step": d2h_bytes // K,
@@ -484,6 +518,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4-single", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "none"],
+                    help="N>1: all-gather the bitsets through peer stores in the cull kernel's epilogue (default) or not at all")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

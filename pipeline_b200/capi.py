@@ -508,6 +508,26 @@ class Tree:
             pass
 
 
+def ipc_get_handle(device_ptr) -> bytes:
+    buf = C.create_string_buffer(64)
+    check(lib().dpcuIpcGetHandle(device_ptr, buf))
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = _vp()
+    check(lib().dpcuIpcOpen(handle, C.byref(p)))
+    return p.value or 0
+
+
+def ipc_close(device_ptr):
+    check(lib().dpcuIpcClose(device_ptr))
+
+
+def enable_peer_access(device, peer):
+    check(lib().dpcuDeviceEnablePeerAccess(device, peer))
+
+
 def scene_generate(seed, first, count, index_base, lower_ptr, extent_ptr, mats_ptr, stream=None):
     check(lib().dpcuSceneGenerate(seed, first, count, index_base, lower_ptr, extent_ptr, mats_ptr,
                                   stream.h if stream else None))
