@@ -186,7 +186,11 @@ int dpcuCullResultDevicePointers(dpcuCullResult *result, const uint32_t **bits, 
 int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 
 /* Tuning / reporting knobs (never change results unless stated). */
-#define DPCU_CULL_OPT_KERNEL        1   /* 0 = auto, 1 = direct 16-byte loads, 2 = TMA-staged pipeline      */
+#define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
+#define DPCU_KERNEL_AUTO    0           /* 1 view: direct; >= 2 views: view-sequential packed                */
+#define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */
+#define DPCU_KERNEL_STAGED  2           /* persistent CTAs, TMA bulk + cp.async staging in shared memory     */
+#define DPCU_KERNEL_VIEWS   3           /* views one after the other, packed f32x2 arithmetic                */
 #define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */

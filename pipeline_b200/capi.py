@@ -6,8 +6,10 @@ library has not been built - there is no fallback of any kind.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -24,6 +26,31 @@ _f32p = C.POINTER(C.c_float)
 _szp = C.POINTER(C.c_size_t)
 
 _lib = None
+
+# Every wrapper that owns a library handle registers here; at interpreter exit the handles are
+# released in dependency order (results before their context, contexts before buffers) while
+# the CUDA runtime is still alive, and finalisers that run later become no-ops.
+_live = weakref.WeakSet()
+_shutdown = False
+_CLOSE_ORDER = ("CullResult", "Cull", "Tree", "Event", "Stream", "HostBuffer", "Buffer")
+
+
+def _register(obj):
+    _live.add(obj)
+
+
+@atexit.register
+def _close_all():
+    global _shutdown
+    objs = list(_live)
+    for name in _CLOSE_ORDER:
+        for o in objs:
+            if type(o).__name__ == name:
+                try:
+                    o.close()
+                except Exception:
+                    pass
+    _shutdown = True
 
 
 class DpcuError(RuntimeError):
@@ -170,6 +197,7 @@ class Buffer:
     def __init__(self, nbytes):
         self.h = _vp()
         check(lib().dpcuBufferCreate(C.byref(self.h), nbytes))
+        _register(self)
         self.nbytes = nbytes
 
     @property
@@ -194,6 +222,8 @@ class Buffer:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:
@@ -206,6 +236,7 @@ class HostBuffer:
     def __init__(self, nbytes, flags=0):
         self.h = _vp()
         check(lib().dpcuHostBufferCreate(C.byref(self.h), nbytes, flags))
+        _register(self)
         self.nbytes = nbytes
         p = _vp()
         check(lib().dpcuHostBufferPointer(self.h, C.byref(p)))
@@ -224,6 +255,8 @@ class HostBuffer:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:
@@ -234,6 +267,7 @@ class Stream:
     def __init__(self, blocking=False, priority=0):
         self.h = _vp()
         check(lib().dpcuStreamCreate(C.byref(self.h), int(blocking), priority))
+        _register(self)
 
     def sync(self):
         check(lib().dpcuStreamSynchronize(self.h))
@@ -258,6 +292,8 @@ class Stream:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:
@@ -268,6 +304,7 @@ class Event:
     def __init__(self, flags=0):
         self.h = _vp()
         check(lib().dpcuEventCreate(C.byref(self.h), flags))
+        _register(self)
 
     def record(self, stream=None):
         check(lib().dpcuEventRecord(self.h, stream.h if stream else None))
@@ -286,6 +323,8 @@ class Event:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:
@@ -298,6 +337,7 @@ class CullResult:
         self.ctx = ctx
         self.h = _vp()
         check(lib().dpcuCullResultCreate(ctx.h, C.byref(self.h)))
+        _register(self)
 
     def bits(self):
         n = self.ctx.count()
@@ -340,6 +380,8 @@ class CullResult:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:
@@ -352,6 +394,7 @@ class Cull:
     def __init__(self, device=0):
         self.h = _vp()
         check(lib().dpcuCullCreate(C.byref(self.h), device))
+        _register(self)
         self.device = device
         self._mat_src = None
 
@@ -433,6 +476,8 @@ class Cull:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:
@@ -444,6 +489,7 @@ class Tree:
     def __init__(self, device=0):
         self.h = _vp()
         check(lib().dpcuTreeCreate(C.byref(self.h), device))
+        _register(self)
         self.n_nodes = 0
 
     def set_topology(self, entries, level_offsets, n_nodes):
@@ -502,6 +548,8 @@ class Tree:
             self.h = None
 
     def __del__(self):
+        if _shutdown:
+            return
         try:
             self.close()
         except Exception:

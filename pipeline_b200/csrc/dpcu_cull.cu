@@ -22,6 +22,8 @@
 // This translation unit is compiled with -fmad=false (exact mode).  dpcu_cull_fma.cu includes
 // it again with DPCU_FMA_VARIANT defined and -fmad=true to provide the reporting-only fast mode.
 #include "cull_math.cuh"
+#include "cull_stage.cuh"
+#include "cull_views.cuh"
 #include "dpcu_internal.h"
 
 #include <new>
@@ -55,6 +57,9 @@ namespace dpcu
     int           buildChanged;
     uint32_t      nSegs;
     uint32_t     *done;      // CTA completion ticket (last CTA scans the segment counters)
+    uint32_t     *chunkCounter;   // staged kernel: next unclaimed chunk of kChunkTiles tiles
+    int           vpFinite;  // every view-projection entry is finite (enables the affine shortcut of cull_views.cuh)
+    unsigned long long onePair;   // (1.0f, 1.0f): runtime multiplier of cull_views.cuh::addProd
     ViewOut       out[NV];
     float4        vp[NV][4];
   };
@@ -182,6 +187,234 @@ namespace dpcu
     }
     if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
+
+
+#ifndef DPCU_FMA_VARIANT
+  // ------------------------------------------------------------------------------------------
+  // K2, view-sequential variant for V >= 2 views (cull_views.cuh): one thread per object, the
+  // OBB is built once, then the views run one after the other through packed f32x2 arithmetic.
+  // Lane v of each warp owns view v's epilogue (previous word, new word, flipped bits, segment
+  // counter, peer stores), so the V epilogues of a warp are one divergent block instead of V.
+  template <int NV>
+  __global__ void __launch_bounds__( kCullThreads, 2 )
+  cullViewsKernel( const __grid_constant__ CullArgs<NV> a )
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    for ( uint32_t tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x )
+    {
+      const uint32_t i        = tile * kCullThreads + threadIdx.x;
+      const bool     live     = i < a.n;
+      const bool     wordLive = ( i - lane ) < a.n;
+      const uint32_t word     = i >> 5;
+
+      uint32_t oldBits = 0;
+      if ( lane < NV && wordLive ) oldBits = a.out[lane].bits[word];
+
+      Obb obb;
+      obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );
+      if ( live )
+      {
+        const float4 lo = ldStream( a.lowerIdx + i );
+        const float4 ex = ldStream( a.extent + i );
+        float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
+        const float4 m0 = __ldg( m + 0 );
+        const float4 m1 = __ldg( m + 1 );
+        const float4 m2 = __ldg( m + 2 );
+        const float4 m3 = __ldg( m + 3 );
+        obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+      }
+      const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
+      const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
+      const ObbPairs ob = broadcastObb( obb );
+
+      const uint32_t myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+
+      if ( lane < NV && wordLive )
+      {
+        ViewOut const &o = a.out[lane];
+        o.bits[word] = myWord;
+        for ( uint32_t p = 0; p < a.nPeers; ++p )
+        {
+          if ( o.peer[p] ) o.peer[p][a.peerWordOffset + word] = myWord;
+        }
+        if ( a.buildChanged )
+        {
+          const uint32_t c = oldBits ^ myWord;
+          o.chg[word] = c;
+          if ( c ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
+        }
+      }
+    }
+    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // K2, staged variant.  Every warp is an independent persistent worker with its own
+  // shared-memory rings over warp-tiles of 32 objects (one bitset word per view):
+  //   P1(q+2)  lane 0: a bulk TMA copy (cp.async.bulk + mbarrier) brings the tile's lowerIdx[32]
+  //            stream (boxes' lower corners + transform indices) into a three-deep ring;
+  //   P2(q+1)  all lanes: wait for that tile's mbarrier, read the transform indices from shared
+  //            memory and gather the matrix rows with 16-byte cp.async into a two-deep ring; lane 0
+  //            adds the bulk copy of extent[32].  Four neighbouring lanes fetch the four rows of
+  //            one matrix, so every global request covers whole 32-byte sectors; rows land
+  //            XOR-swizzled so that both the copy and the later 128-bit reads are free of bank
+  //            conflicts;
+  //   C(q)     all lanes: the object from shared memory -> OBB -> views -> ballots -> epilogue.
+  // Every load is issued at least one tile-time before its use without spending registers on
+  // prefetching, no CTA-wide barrier exists, and tiles are handed out dynamically in chunks of 32
+  // warp-tiles (1024 objects = one 128-byte line of each bitset) from a global counter, so all
+  // SMs stay full to the end.  6.6 KiB of shared memory per warp -> 4 CTAs (32 warps) per SM.
+  constexpr uint32_t kChunkTiles = 32;            // warp-tiles per claimed chunk
+  constexpr uint32_t kNoTile     = 0xffffffffu;
+
+  struct alignas( 128 ) WarpRing
+  {
+    float4   lo[3][32];        // ring 3: lowerIdx tiles
+    float4   ex[2][32];        // ring 2: extent tiles
+    float4   m[2][128];        // ring 2: matrix of object o at o*4, 16-byte chunks XOR-swizzled by (o>>1)&3
+    uint64_t loFull[3];        // mbarriers: bytes of the bulk copies have landed
+    uint64_t exFull[2];
+  };
+
+  __device__ __forceinline__ uint32_t swizzledRow( uint32_t o, uint32_t r )
+  {
+    return o * 4u + ( r ^ ( ( o >> 1 ) & 3u ) );
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void storeWord( ViewOut const &o, CullArgs<NV> const &a, uint32_t word, uint32_t nw, uint32_t old )
+  {
+    o.bits[word] = nw;
+    for ( uint32_t p = 0; p < a.nPeers; ++p )
+    {
+      if ( o.peer[p] ) o.peer[p][a.peerWordOffset + word] = nw;
+    }
+    if ( a.buildChanged )
+    {
+      const uint32_t c = old ^ nw;
+      o.chg[word] = c;
+      if ( c ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
+    }
+  }
+
+  template <int NV>
+  __global__ void __launch_bounds__( kCullThreads, 4 )
+  cullStagedKernel( const __grid_constant__ CullArgs<NV> a )
+  {
+    extern __shared__ __align__( 128 ) unsigned char smemRaw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    WarpRing &ring = reinterpret_cast<WarpRing *>( smemRaw )[warp];
+
+    const uint32_t nTiles     = ( a.n + 31u ) >> 5;                            // warp-tiles
+    const uint32_t nChunks    = ( nTiles + kChunkTiles - 1 ) / kChunkTiles;
+    const uint32_t totalWarps = gridDim.x * ( kCullThreads / 32 );
+    // tile sequence of this warp: chunks of kChunkTiles tiles, the first one static, the following
+    // ones claimed from the global counter one chunk ahead of their use (lane 0 holds the claim)
+    uint32_t curChunk = blockIdx.x * ( kCullThreads / 32 ) + warp, sub = 0, claimed = 0;
+    auto claim = [&]() { if ( lane == 0 ) claimed = ( curChunk < nChunks ) ? totalWarps + atomicAdd( a.chunkCounter, 1u ) : nChunks; };
+    auto nextTile = [&]() -> uint32_t
+    {
+      if ( sub == kChunkTiles )
+      {
+        curChunk = __shfl_sync( 0xffffffffu, claimed, 0 );
+        claim();
+        sub = 0;
+      }
+      const uint32_t t = curChunk * kChunkTiles + sub++;
+      return ( curChunk < nChunks && t < nTiles ) ? t : kNoTile;
+    };
+    // P1: lowerIdx of `tile` (sequence index q) -> lo ring
+    auto issueLower = [&]( uint32_t q, uint32_t tile )
+    {
+      if ( tile == kNoTile || lane != 0 ) return;
+      const uint32_t first = tile << 5, bytes = min( 32u, a.n - first ) * 16u, s = q % 3u;
+      mbarArriveExpectTx( &ring.loFull[s], bytes );
+      tmaLoad1d( ring.lo[s], a.lowerIdx + first, bytes, &ring.loFull[s] );
+    };
+    // P2: extent and gathered matrices of `tile` (sequence index q); returns the previous
+    // visibility word lane v will need in the epilogue of that tile
+    auto issueGather = [&]( uint32_t q, uint32_t tile ) -> uint32_t
+    {
+      uint32_t old = 0;
+      if ( tile != kNoTile )
+      {
+        const uint32_t first = tile << 5, s3 = q % 3u, s2 = q & 1u;
+        if ( lane == 0 )
+        {
+          const uint32_t bytes = min( 32u, a.n - first ) * 16u;
+          mbarArriveExpectTx( &ring.exFull[s2], bytes );
+          tmaLoad1d( ring.ex[s2], a.extent + first, bytes, &ring.exFull[s2] );
+        }
+        if ( lane < NV ) old = a.out[lane].bits[tile];
+        mbarWait( &ring.loFull[s3], ( q / 3u ) & 1u );
+#pragma unroll
+        for ( uint32_t j = 0; j < 4; ++j )
+        {
+          const uint32_t o = j * 8u + ( lane >> 2 ), r = lane & 3u;
+          if ( first + o < a.n )
+          {
+            const uint32_t idx = __float_as_uint( ring.lo[s3][o].w );
+            cpAsync16( &ring.m[s2][swizzledRow( o, r )], a.mats + 4ull * idx + r );
+          }
+        }
+      }
+      cpAsyncCommit();
+      return old;
+    };
+
+    if ( lane == 0 )
+    {
+      for ( int s = 0; s < 3; ++s ) mbarInit( &ring.loFull[s], 1 );
+      for ( int s = 0; s < 2; ++s ) mbarInit( &ring.exFull[s], 1 );
+      mbarInitFence();
+    }
+    claim();
+    __syncwarp();
+    uint32_t tile0 = nextTile(), tile1 = nextTile();
+    issueLower( 0, tile0 );
+    issueLower( 1, tile1 );
+    uint32_t old0 = issueGather( 0, tile0 );
+
+    for ( uint32_t q = 0; tile0 != kNoTile; ++q )
+    {
+      __syncwarp();                                        // every lane has finished reading the ring slots of tile q-1
+      const uint32_t tile2 = nextTile();
+      issueLower( q + 2, tile2 );                          // P1(q+2)
+      const uint32_t old1 = issueGather( q + 1, tile1 );   // P2(q+1)
+      cpAsyncWait<1>();                                    // rows of tile q (committed one iteration ago) have landed ...
+      mbarWait( &ring.exFull[q & 1u], ( q >> 1 ) & 1u );   // ... and so has its extent stream
+      __syncwarp();                                        // ... for every lane of the warp that fetched them
+
+      const bool live = ( tile0 << 5 ) + lane < a.n;
+      Obb obb;
+      obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );
+      if ( live )
+      {
+        const float4 lo = ring.lo[q % 3u][lane];
+        const float4 ex = ring.ex[q & 1u][lane];
+        float4 const *m = ring.m[q & 1u];
+        obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m[swizzledRow( lane, 0 )], m[swizzledRow( lane, 1 )],
+                       m[swizzledRow( lane, 2 )], m[swizzledRow( lane, 3 )] );
+      }
+      uint32_t myWord = 0;
+      if ( NV == 1 )
+      {
+        myWord = __ballot_sync( 0xffffffffu, obbVisible( obb, a.vp[0][0], a.vp[0][1], a.vp[0][2], a.vp[0][3] ) & live );
+      }
+      else
+      {
+        const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
+        const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
+        const ObbPairs ob = broadcastObb( obb );
+        myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+      }
+      if ( lane < NV ) storeWord<NV>( a.out[lane], a, tile0, myWord, old0 );
+      tile0 = tile1; tile1 = tile2;
+      old0 = old1;
+    }
+    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+  }
+#endif
 
 #ifndef DPCU_FMA_VARIANT
   // ------------------------------------------------------------------------------------------
@@ -403,7 +636,7 @@ struct dpcuCullResult
   size_t   capWords = 0;
   size_t   nSegsCap = 0;
   bool     ran = false;          // a changed list exists
-  cudaStream_t lastStream = nullptr;
+  dpcu::StreamFence done;        // last cull / bit move submitted for this result
   uint32_t *peer[dpcu::kMaxPeers] = { nullptr };
   int      nPeers = 0;
   size_t   peerWordOffset = 0;
@@ -422,6 +655,8 @@ struct dpcuCull
   cudaStream_t stream = nullptr;
   dpcu::DeviceArray lowerIdx, extent, mats, scratch, maxIndex;
   dpcu::PinnedArray staging;
+  dpcu::StreamFence uploads;     // object / matrix updates submitted on `stream`
+  dpcu::StreamFence lastRun;     // last cull submitted (possibly on a caller stream); updates are ordered after it
   float const *boundMats = nullptr;      // borrowed device matrices (dpcuCullBindMatrices)
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
@@ -519,15 +754,39 @@ namespace dpcu
       args.peerWordOffset = uint32_t( r->peerWordOffset );
       memcpy( args.vp[v], vps + 16 * v, 64 );
     }
+    // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
+    // issue-bound and the view-sequential packed kernel (cull_views.cuh) is the faster exact form
+    const bool useStaged = !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
+    const bool useViews  = !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
+    args.chunkCounter = results[0]->donePtr() + 1;
+    const size_t stagedSmem = sizeof( WarpRing ) * ( kCullThreads / 32 );
+    if ( useStaged ) DPCU_CUDA( cudaFuncSetAttribute( cullStagedKernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( stagedSmem ) ) );
+    args.vpFinite = 1;
+    args.onePair  = 0x3f8000003f800000ull;
+    for ( int k = 0; k < 16 * NV; ++k )
+    {
+      uint32_t u;
+      memcpy( &u, vps + k, 4 );
+      if ( ( u & 0x7f800000u ) == 0x7f800000u ) args.vpFinite = 0;
+    }
     int perSm = ctx->optCtasPerSm;
     if ( perSm <= 0 )
     {
       if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
+      else if ( useStaged ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullStagedKernel<NV>, kCullThreads, stagedSmem );
+      else if ( useViews ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV>, kCullThreads, 0 );
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullDirectKernel<NV>, kCullThreads, 0 );
       if ( perSm <= 0 ) perSm = 1;
     }
     int grid = ctx->smCount * perSm;
     if ( uint32_t( grid ) > args.nTiles ) grid = int( args.nTiles );
+    if ( useStaged )
+    {
+      // one chunk (kChunkTiles warp-tiles = 1024 objects) per warp to start with
+      const uint32_t nChunks = uint32_t( divUp( divUp( ctx->n, 32 ), kChunkTiles ) );
+      const uint32_t ctasForChunks = uint32_t( divUp( nChunks, kCullThreads / 32 ) );
+      if ( uint32_t( grid ) > ctasForChunks ) grid = int( ctasForChunks );
+    }
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     if ( ctx->optProfile )
     {
@@ -545,6 +804,16 @@ namespace dpcu
     if ( ctx->optFma )
     {
       DPCU_CUDA( launchCullDirectFma<NV>( args, grid, stream ) );
+    }
+    else if ( useStaged )
+    {
+      cullStagedKernel<NV><<<grid, kCullThreads, stagedSmem, stream>>>( args );
+      DPCU_CUDA( cudaGetLastError() );
+    }
+    else if ( useViews )
+    {
+      cullViewsKernel<NV><<<grid, kCullThreads, 0, stream>>>( args );
+      DPCU_CUDA( cudaGetLastError() );
     }
     else
     {
@@ -590,6 +859,9 @@ extern "C"
     cudaStreamSynchronize( ctx->stream );
     ctx->lowerIdx.release(); ctx->extent.release(); ctx->mats.release(); ctx->scratch.release(); ctx->maxIndex.release();
     ctx->staging.release();
+    ctx->uploads.destroy();
+    ctx->lastRun.hostWait();
+    ctx->lastRun.destroy();
     for ( cudaEvent_t e : ctx->profEvents ) cudaEventDestroy( e );
     cudaStreamDestroy( ctx->stream );
     delete ctx;
@@ -605,6 +877,7 @@ extern "C"
     DPCU_REQUIRE( memspace == DPCU_MEM_DEVICE || transformIndex || !count, "transformIndex may only be NULL for device memory" );
     if ( !count ) return DPCU_OK;
     dpcu::DeviceGuard guard( ctx->device );
+    DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
     float4 const *lo = nullptr, *ex = nullptr;
     uint32_t const *ti = nullptr;
     if ( memspace == DPCU_MEM_HOST )
@@ -643,6 +916,7 @@ extern "C"
     DPCU_REQUIRE( n < ( size_t( 1 ) << 32 ), "object count must fit 32 bits" );
     DPCU_REQUIRE( memspace == DPCU_MEM_HOST || memspace == DPCU_MEM_DEVICE, "bad memspace" );
     dpcu::DeviceGuard guard( ctx->device );
+    DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
     DPCU_TRY( ctx->lowerIdx.reserve( ( n ? n : 1 ) * 16, false, ctx->stream ) );
     DPCU_TRY( ctx->extent.reserve( ( n ? n : 1 ) * 16, false, ctx->stream ) );
     ctx->n = n;
@@ -667,6 +941,7 @@ extern "C"
     DPCU_REQUIRE( count < ( size_t( 1 ) << 32 ), "matrix count must fit 32 bits" );
     DPCU_REQUIRE( memspace == DPCU_MEM_HOST || memspace == DPCU_MEM_DEVICE, "bad memspace" );
     dpcu::DeviceGuard guard( ctx->device );
+    DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
     DPCU_TRY( ctx->mats.reserve( ( count ? count : 1 ) * 64, false, ctx->stream ) );
     ctx->boundMats = nullptr;
     ctx->nMats = count;
@@ -697,6 +972,7 @@ extern "C"
     DPCU_REQUIRE( memspace == DPCU_MEM_HOST, "only host source matrices are supported for batched updates" );
     if ( !n ) return DPCU_OK;
     dpcu::DeviceGuard guard( ctx->device );
+    DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
     // pack [matrices | indices] into pinned staging, skipping indices past the matrix count
     // (markMatrixDirty ignores those, dp/culling/GroupBitSet.h:140-150)
     DPCU_TRY( ctx->staging.reserve( n * 68 ) );
@@ -749,7 +1025,6 @@ extern "C"
     dpcuCullResult *r = new ( std::nothrow ) dpcuCullResult;
     if ( !r ) return dpcu::fail( DPCU_ERR_OUT_OF_MEMORY, "dpcuCullResultCreate: host allocation failed" );
     r->ctx = ctx;
-    r->lastStream = ctx->stream;
     r->next = ctx->results;
     if ( ctx->results ) ctx->results->prev = r;
     ctx->results = r;
@@ -762,7 +1037,8 @@ extern "C"
     if ( !r ) return DPCU_OK;
     dpcuCull *ctx = r->ctx;
     dpcu::DeviceGuard guard( ctx->device );
-    cudaStreamSynchronize( r->lastStream );
+    r->done.hostWait();
+    r->done.destroy();
     r->bits.release(); r->chg.release(); r->changed.release(); r->counters.release();
     if ( r->prev ) r->prev->next = r->next; else ctx->results = r->next;
     if ( r->next ) r->next->prev = r->prev;
@@ -781,7 +1057,12 @@ extern "C"
     }
     dpcu::DeviceGuard guard( ctx->device );
     cudaStream_t s = stream ? stream->stream : ctx->stream;
-    if ( s != ctx->stream ) DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );   // uploads happened on the context stream
+    if ( s != ctx->stream )
+    {
+      // uploads were submitted on the context stream: order this run after them on the device
+      DPCU_CUDA( ctx->uploads.record( ctx->stream ) );
+      DPCU_CUDA( ctx->uploads.orderBefore( s ) );
+    }
     const size_t n = ctx->n;
     if ( n )
     {
@@ -794,8 +1075,7 @@ extern "C"
     for ( int v = 0; v < nViews; ++v )
     {
       dpcuCullResult *r = results[v];
-      if ( r->lastStream != s ) DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
-      r->lastStream = s;
+      DPCU_CUDA( r->done.orderBefore( s ) );      // after this result's previous cull / bit moves, wherever they ran
       DPCU_TRY( dpcu::ensureResultCapacity( r, n, s ) );
       if ( r->n != n )
       {
@@ -811,7 +1091,11 @@ extern "C"
       DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, ( nSegs + 1 + 4 ) * 4, s ) );
       r->ran = true;
     }
-    if ( !n ) return DPCU_OK;
+    if ( !n )
+    {
+      for ( int v = 0; v < nViews; ++v ) DPCU_CUDA( results[v]->done.record( s ) );
+      return DPCU_OK;
+    }
     int rc = DPCU_OK;
     switch ( nViews )
     {
@@ -843,6 +1127,8 @@ extern "C"
       DPCU_CUDA( cudaGetLastError() );
       ++ctx->launches;
     }
+    for ( int v = 0; v < nViews; ++v ) DPCU_CUDA( results[v]->done.record( s ) );
+    if ( s != ctx->stream ) DPCU_CUDA( ctx->lastRun.record( s ) );
     return DPCU_OK;
   }
 
@@ -853,8 +1139,10 @@ extern "C"
     DPCU_REQUIRE( nWords >= have, "nWords smaller than ceil(n/32)" );
     if ( !have ) return DPCU_OK;
     dpcu::DeviceGuard guard( r->ctx->device );
-    DPCU_CUDA( cudaMemcpyAsync( hostWords, r->bits.ptr, have * 4, cudaMemcpyDeviceToHost, r->lastStream ) );
-    DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    cudaStream_t s = r->ctx->stream;
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    DPCU_CUDA( cudaMemcpyAsync( hostWords, r->bits.ptr, have * 4, cudaMemcpyDeviceToHost, s ) );
+    DPCU_CUDA( cudaStreamSynchronize( s ) );
     return DPCU_OK;
   }
 
@@ -866,8 +1154,10 @@ extern "C"
     if ( !r->ctx->optChanged ) return dpcu::fail( DPCU_ERR_NOT_READY, "changed list disabled (DPCU_CULL_OPT_CHANGED_LIST = 0)" );
     dpcu::DeviceGuard guard( r->ctx->device );
     uint32_t c = 0;
-    DPCU_CUDA( cudaMemcpyAsync( &c, r->countPtr(), 4, cudaMemcpyDeviceToHost, r->lastStream ) );
-    DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    cudaStream_t s = r->ctx->stream;
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    DPCU_CUDA( cudaMemcpyAsync( &c, r->countPtr(), 4, cudaMemcpyDeviceToHost, s ) );
+    DPCU_CUDA( cudaStreamSynchronize( s ) );
     *count = c;
     return DPCU_OK;
   }
@@ -881,8 +1171,9 @@ extern "C"
     {
       DPCU_REQUIRE( hostIndices, "hostIndices is NULL" );
       dpcu::DeviceGuard guard( r->ctx->device );
-      DPCU_CUDA( cudaMemcpyAsync( hostIndices, r->changed.ptr, c * 4, cudaMemcpyDeviceToHost, r->lastStream ) );
-      DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+      cudaStream_t s = r->ctx->stream;     // already ordered after the cull by dpcuCullResultGetChangedCount
+      DPCU_CUDA( cudaMemcpyAsync( hostIndices, r->changed.ptr, c * 4, cudaMemcpyDeviceToHost, s ) );
+      DPCU_CUDA( cudaStreamSynchronize( s ) );
     }
     return DPCU_OK;
   }
@@ -894,8 +1185,10 @@ extern "C"
     if ( groupIndex >= r->n ) return DPCU_OK;
     dpcu::DeviceGuard guard( r->ctx->device );
     uint32_t w = 0;
-    DPCU_CUDA( cudaMemcpyAsync( &w, static_cast<uint32_t *>( r->bits.ptr ) + ( groupIndex >> 5 ), 4, cudaMemcpyDeviceToHost, r->lastStream ) );
-    DPCU_CUDA( cudaStreamSynchronize( r->lastStream ) );
+    cudaStream_t s = r->ctx->stream;
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    DPCU_CUDA( cudaMemcpyAsync( &w, static_cast<uint32_t *>( r->bits.ptr ) + ( groupIndex >> 5 ), 4, cudaMemcpyDeviceToHost, s ) );
+    DPCU_CUDA( cudaStreamSynchronize( s ) );
     *visible = int( ( w >> ( groupIndex & 31 ) ) & 1u );
     return DPCU_OK;
   }
@@ -906,8 +1199,11 @@ extern "C"
     if ( newIndex >= r->n ) return DPCU_OK;
     dpcu::DeviceGuard guard( r->ctx->device );
     uint32_t o = oldIndex < ( size_t( 1 ) << 32 ) ? uint32_t( oldIndex ) : 0xffffffffu;
-    dpcu::moveBitKernel<<<1, 1, 0, r->lastStream>>>( static_cast<uint32_t *>( r->bits.ptr ), uint32_t( r->n ), o, uint32_t( newIndex ) );
+    cudaStream_t s = r->ctx->stream;
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    dpcu::moveBitKernel<<<1, 1, 0, s>>>( static_cast<uint32_t *>( r->bits.ptr ), uint32_t( r->n ), o, uint32_t( newIndex ) );
     DPCU_CUDA( cudaGetLastError() );
+    DPCU_CUDA( r->done.record( s ) );
     ++r->ctx->launches;
     return DPCU_OK;
   }
@@ -988,7 +1284,7 @@ extern "C"
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     switch ( option )
     {
-      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 2, "kernel must be 0..2" ); ctx->optKernel = value; break;
+      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 3, "kernel must be 0..3" ); ctx->optKernel = value; break;
       case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;

@@ -54,6 +54,26 @@ namespace dpcu
   };
 
   inline size_t divUp( size_t a, size_t b ) { return ( a + b - 1 ) / b; }
+
+  // "The work last submitted for this object", as an event: unlike a remembered cudaStream_t it
+  // stays valid after the caller destroyed the stream the work ran on.
+  struct StreamFence
+  {
+    cudaEvent_t event = nullptr;
+    bool        pending = false;
+    cudaError_t record( cudaStream_t s )
+    {
+      cudaError_t e = cudaSuccess;
+      if ( !event ) e = cudaEventCreateWithFlags( &event, cudaEventDisableTiming );
+      if ( e == cudaSuccess ) e = cudaEventRecord( event, s );
+      pending = ( e == cudaSuccess );
+      return e;
+    }
+    // make stream s wait for the recorded work (device-side ordering, no host block)
+    cudaError_t orderBefore( cudaStream_t s ) const { return pending ? cudaStreamWaitEvent( s, event, 0 ) : cudaSuccess; }
+    void hostWait() const { if ( pending ) cudaEventSynchronize( event ); }
+    void destroy() { if ( event ) cudaEventDestroy( event ); event = nullptr; pending = false; }
+  };
 }
 
 struct dpcuStream

@@ -86,7 +86,8 @@ struct dpcuTree
   size_t       numEntries = 0;
   std::vector<uint32_t> levelOffsets;
   uint64_t     launches = 0;
-  cudaStream_t lastStream = nullptr;
+  dpcu::StreamFence done;        // last compute submitted
+  dpcu::StreamFence uploads;
 };
 
 extern "C"
@@ -105,7 +106,6 @@ extern "C"
     t->device = device;
     cudaError_t e = cudaStreamCreateWithFlags( &t->stream, cudaStreamNonBlocking );
     if ( e != cudaSuccess ) { delete t; return dpcu::failCuda( e, "cudaStreamCreateWithFlags", __FILE__, __LINE__ ); }
-    t->lastStream = t->stream;
     *out = t;
     return DPCU_OK;
   }
@@ -115,7 +115,9 @@ extern "C"
     if ( !t ) return DPCU_OK;
     dpcu::DeviceGuard guard( t->device );
     cudaStreamSynchronize( t->stream );
-    if ( t->lastStream != t->stream ) cudaStreamSynchronize( t->lastStream );
+    t->done.hostWait();
+    t->done.destroy();
+    t->uploads.destroy();
     t->local.release(); t->world.release(); t->entries.release(); t->dirtyLocal.release(); t->dirtyWorld.release(); t->scratch.release();
     cudaStreamDestroy( t->stream );
     delete t;
@@ -138,6 +140,7 @@ extern "C"
     }
     dpcu::DeviceGuard guard( t->device );
     cudaStream_t s = t->stream;
+    DPCU_CUDA( t->done.orderBefore( s ) );            // a compute may still be running on a caller stream
     size_t oldNodes = t->numNodes;
     size_t oldWords = dpcu::divUp( oldNodes, 32 ), newWords = dpcu::divUp( numNodes, 32 );
     DPCU_TRY( t->local.reserve( numNodes * 64, true, s ) );
@@ -179,6 +182,7 @@ extern "C"
     if ( !count ) return DPCU_OK;
     dpcu::DeviceGuard guard( t->device );
     size_t words = ( ( first + count - 1 ) >> 5 ) - ( first >> 5 ) + 1;
+    DPCU_CUDA( t->done.orderBefore( t->stream ) );    // the previous compute clears the dirty bits at its end
     dpcu::treeMarkRangeKernel<<<unsigned( dpcu::divUp( words, 256 ) ), 256, 0, t->stream>>>(
       static_cast<uint32_t *>( t->dirtyLocal.ptr ), uint32_t( first ), uint32_t( count ) );
     DPCU_CUDA( cudaGetLastError() );
@@ -195,6 +199,7 @@ extern "C"
     if ( !count ) return DPCU_OK;
     dpcu::DeviceGuard guard( t->device );
     char *dst = static_cast<char *>( t->local.ptr ) + first * 64;
+    DPCU_CUDA( t->done.orderBefore( t->stream ) );
     DPCU_CUDA( cudaMemcpyAsync( dst, matrices, count * 64, memspace == DPCU_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, t->stream ) );
     DPCU_TRY( dpcuTreeMarkDirty( t, first, count ) );
     if ( memspace == DPCU_MEM_HOST ) DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
@@ -210,6 +215,7 @@ extern "C"
     if ( !n ) return DPCU_OK;
     for ( size_t i = 0; i < n; ++i ) DPCU_REQUIRE( indices[i] < t->numNodes, "node index out of range" );
     dpcu::DeviceGuard guard( t->device );
+    DPCU_CUDA( t->done.orderBefore( t->stream ) );
     DPCU_TRY( t->scratch.reserve( n * 68, false, t->stream ) );
     char *s = static_cast<char *>( t->scratch.ptr );
     DPCU_CUDA( cudaMemcpyAsync( s, matrices, n * 64, cudaMemcpyHostToDevice, t->stream ) );
@@ -229,9 +235,12 @@ extern "C"
     DPCU_REQUIRE( t->numNodes >= 1, "no topology set" );
     dpcu::DeviceGuard guard( t->device );
     cudaStream_t s = stream ? stream->stream : t->stream;
-    if ( s != t->stream ) DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
-    if ( t->lastStream != s ) DPCU_CUDA( cudaStreamSynchronize( t->lastStream ) );
-    t->lastStream = s;
+    if ( s != t->stream )
+    {
+      DPCU_CUDA( t->uploads.record( t->stream ) );      // topology / local-matrix updates ran on the tree's stream
+      DPCU_CUDA( t->uploads.orderBefore( s ) );
+    }
+    DPCU_CUDA( t->done.orderBefore( s ) );
     size_t words = dpcu::divUp( t->numNodes, 32 );
     // the previous compute's published set is dropped now (the reference clears it right after notifying, Tree.cpp:163-164)
     DPCU_CUDA( cudaMemsetAsync( t->dirtyWorld.ptr, 0, words * 4, s ) );
@@ -247,6 +256,7 @@ extern "C"
       ++t->launches;
     }
     DPCU_CUDA( cudaMemsetAsync( t->dirtyLocal.ptr, 0, words * 4, s ) );   // Tree.cpp:163
+    DPCU_CUDA( t->done.record( s ) );
     return DPCU_OK;
   }
 
@@ -272,8 +282,9 @@ extern "C"
     DPCU_REQUIRE( first + count <= t->numNodes, "range exceeds node count" );
     if ( !count ) return DPCU_OK;
     dpcu::DeviceGuard guard( t->device );
-    DPCU_CUDA( cudaMemcpyAsync( hostMatrices, static_cast<char *>( t->world.ptr ) + first * 64, count * 64, cudaMemcpyDeviceToHost, t->lastStream ) );
-    DPCU_CUDA( cudaStreamSynchronize( t->lastStream ) );
+    DPCU_CUDA( t->done.orderBefore( t->stream ) );
+    DPCU_CUDA( cudaMemcpyAsync( hostMatrices, static_cast<char *>( t->world.ptr ) + first * 64, count * 64, cudaMemcpyDeviceToHost, t->stream ) );
+    DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
     return DPCU_OK;
   }
 
@@ -283,8 +294,9 @@ extern "C"
     size_t have = dpcu::divUp( t->numNodes, 32 );
     DPCU_REQUIRE( nWords >= have, "nWords smaller than ceil(numNodes/32)" );
     dpcu::DeviceGuard guard( t->device );
-    DPCU_CUDA( cudaMemcpyAsync( hostWords, t->dirtyWorld.ptr, have * 4, cudaMemcpyDeviceToHost, t->lastStream ) );
-    DPCU_CUDA( cudaStreamSynchronize( t->lastStream ) );
+    DPCU_CUDA( t->done.orderBefore( t->stream ) );
+    DPCU_CUDA( cudaMemcpyAsync( hostWords, t->dirtyWorld.ptr, have * 4, cudaMemcpyDeviceToHost, t->stream ) );
+    DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
     return DPCU_OK;
   }
 

@@ -201,6 +201,98 @@ def test_multi_view_equals_single_views(capi, port):
     ctx.close()
 
 
+# ------------------------------------------------------------------ both exact kernel forms, 1..8 views
+KERNELS = {"direct": 1, "staged": 2, "views": 3}
+
+
+def _views_for(nv, extra=()):
+    cams = list(scenes.cube_map_cameras()) + [scenes.camera_c2(), scenes.orbit_camera(3)]
+    cams = list(extra) + cams
+    return np.ascontiguousarray(np.stack(cams[:nv]), np.float32)
+
+
+def _check_views(capi, port, kernel, lower4, extent4, tidx, mats, vps, frames=1):
+    n = len(lower4)
+    ctx = capi.Cull(0)
+    ctx.set_option(capi.OPT_KERNEL, KERNELS[kernel])
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    res = [ctx.result_create() for _ in range(len(vps))]
+    state = [port.result_resize(np.zeros(0, np.uint32), 0, n) for _ in vps]
+    for f in range(frames):
+        use = vps if f % 2 == 0 else vps[::-1].copy()
+        ctx.run(res, use)
+        for v in range(len(vps)):
+            want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), use[v])
+            got = res[v].bits()
+            assert np.array_equal(got, want), "%s kernel, %d views, view %d, frame %d: %d bits differ" % (
+                kernel, len(vps), v, f, popcount(got ^ want))
+            assert np.array_equal(res[v].changed(), port.update_changed(want, state[v], n)), (kernel, v, f)
+    for r in res:
+        r.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+@pytest.mark.parametrize("nv", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_view_counts_both_kernels(capi, port, kernel, nv):
+    n = 30011                                  # ragged: partial last warp and tile
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C4)
+    _check_views(capi, port, kernel, lower4, extent4, tidx, mats, _views_for(nv), frames=2)
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_non_affine_and_special_values_multi_view(capi, port, kernel):
+    """Projective / NaN / Inf world matrices force the views kernel's general path, the affine
+    block at the front takes the shortcut, and warps that straddle the two must agree as well."""
+    for seed in (61, 62, 63):
+        lower4, extent4, upper4, mats, tidx, vps = cases.special_case(6000, seed=seed)
+        rng = np.random.RandomState(seed)
+        # interleave: every 5th object of the affine block gets a projective last column
+        mats = mats.copy()
+        mats[0:1500:5, :, 3] = rng.choice(np.array([0.0, 1.0, -1.0, 0.5], np.float32), size=(300, 4))
+        # -0 in the last column and a translation-only w must still count as affine (== compares)
+        mats[1:1500:5, 0, 3] = np.float32(-0.0)
+        views = _views_for(6, extra=vps)
+        _check_views(capi, port, kernel, lower4, extent4, tidx, mats, views)
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_non_finite_view_projection(capi, port, kernel):
+    """An Inf / NaN entry in any view-projection switches the affine shortcut off (0 * Inf = NaN
+    must be computed, not skipped)."""
+    n = 20000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n)
+    vps = _views_for(4)
+    vps[1, 3, 2] = np.inf
+    vps[2, 3, 3] = np.nan
+    vps[3, 3, 0] = -np.inf
+    _check_views(capi, port, kernel, lower4, extent4, tidx, mats, vps)
+
+
+def test_views_kernel_four_million_objects_six_views(capi, port):
+    """Volume test: 2^22 random objects x 6 views = 25 M object-view decisions, every one equal
+    to the oracle's.  (A contracted multiply-add anywhere in the packed arithmetic flips a few
+    boundary objects per million - see test_fma_mode_reports_disagreements.)"""
+    n = 1 << 22
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C4)
+    vps = _views_for(6)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    assert ctx.get_option(capi.OPT_KERNEL) == 0          # auto -> views kernel for 6 views
+    res = [ctx.result_create() for _ in range(6)]
+    ctx.run(res, vps)
+    flat = mats.reshape(-1)
+    for v in range(6):
+        want = port.cull_bits(lower4, extent4, tidx, flat, vps[v], threads=8)
+        got = res[v].bits()
+        assert np.array_equal(got, want), "view %d: %d of %d objects differ" % (v, popcount(got ^ want), n)
+    for r in res:
+        r.close()
+    ctx.close()
+
+
 def test_matrix_updates_vs_port(capi, port):
     lower4, extent4, upper4, mats, tidx = cases.random_case(4096)
     mats = mats.copy()

@@ -57,9 +57,13 @@ def main():
     t = np.median(times)
     nchg = sum(r.changed_count() for r in res) if a.changed else 0
     bytes_alg = n * (96 + 0.25 * a.views) + 4 * nchg
+    import zlib
+    crc = 0
+    for r in res:
+        crc = zlib.crc32(r.bits().tobytes(), crc)
     vis = int(np.unpackbits(res[0].bits().view(np.uint8)).sum())
-    print("n=%d views=%d kernel=%d ctas=%d fma=%d changed=%d: median %.4f ms (min %.4f) -> %.2f Gobj/s, %.0f GB/s algorithmic; visible %.1f%% changed %d"
-          % (n, a.views, a.kernel, a.ctas, a.fma, a.changed, t, min(times), n / t / 1e6, bytes_alg / t / 1e6, 100.0 * vis / n, nchg))
+    print("n=%d views=%d kernel=%d ctas=%d fma=%d changed=%d: median %.4f ms (min %.4f) -> %.2f Gobj/s, %.0f GB/s algorithmic; visible %.1f%% changed %d bits-crc %08x"
+          % (n, a.views, a.kernel, a.ctas, a.fma, a.changed, t, min(times), n / t / 1e6, bytes_alg / t / 1e6, 100.0 * vis / n, nchg, crc))
 
 
 if __name__ == "__main__":
