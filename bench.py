@@ -350,8 +350,9 @@ def run_ours(args, rank, world, local_rank):
     def step(f, s=stream):
         if tree is not None:
             tree.mark_dirty(1, tree.n_nodes - 1)   # every local matrix "rewritten" this frame
-            tree.compute(s)
-        ctx.run(results, cams[f], s)
+            ctx.run_with_tree(tree, results, cams[f], s)   # levels 0..2 propagate, the leaf level runs inside the cull kernel
+        else:
+            ctx.run(results, cams[f], s)
 
     sampler = ClockSampler(device)
     sampler.start()
@@ -412,8 +413,9 @@ def run_ours(args, rank, world, local_rank):
         hvp[:] = cams[f].reshape(-1)           # the step's input lives in pinned host memory
         if tree is not None:
             tree.mark_dirty(1, tree.n_nodes - 1)
-            tree.compute(stream)
-        ctx.run(results, hvp, stream)
+            ctx.run_with_tree(tree, results, hvp, stream)
+        else:
+            ctx.run(results, hvp, stream)
         d2h = 0
         for v in range(views):
             capi.check(L.dpcuCullResultGetBits(results[v].h, hb[v].ctypes.data_as(u32p), n_words))
@@ -458,6 +460,11 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- roofline of the dominant kernel (K2, the cull kernel)
     peak, peak_src = measured_peak()
     alg_bytes = n_per * (96.0 + 0.25 * views)            # per launch, per GPU
+    kernel_name = "cullDirectKernel<1>" if views == 1 else "cullViewsKernel<%d>" % views
+    if tree is not None:
+        # fused leaf level: local 64 + entry 8 + world write 64 + AABB 32 + bits, parents (1/16 of the leaves) 64 each
+        alg_bytes = n_per * (64.0 + 8.0 + 64.0 + 32.0 + 0.25 * views) + C3_LEVELS[-2] * 64.0
+        kernel_name = "cullFusedLeafKernel<%d>" % views
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = alg_bytes / (k_avg_ms / 1000.0) / 1e9
     traffic = None
@@ -468,15 +475,16 @@ def run_ours(args, rank, world, local_rank):
                 traffic = p["dram_bytes_read"] + p["dram_bytes_write"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "cullDirectKernel<%d>" % views, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n),
                 "step_share": k_ms / ms_total if ms_total else None}
     if tree is not None:
-        nodes = sum(C3_LEVELS)
-        alg_tree = nodes * 136.0 + (1 + sum(C3_LEVELS[:-1])) * 64.0
-        roofline["step_algorithmic_bytes"] = alg_tree + alg_bytes
-        roofline["step_achieved"] = (alg_tree + alg_bytes) / (ms_per_step / 1000.0) / 1e9
+        upper = sum(C3_LEVELS[:-1])
+        alg_upper = upper * 136.0 + (1 + sum(C3_LEVELS[:-2])) * 64.0     # levels 0..2: K1 launches
+        roofline["step_algorithmic_bytes"] = alg_upper + alg_bytes       # 3.05 GB: the fused figure of SURVEY.md 8d
+        roofline["step_achieved"] = (alg_upper + alg_bytes) / (ms_per_step / 1000.0) / 1e9
+        roofline["step_frac"] = roofline["step_achieved"] / peak
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -195,6 +195,8 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */
 #define DPCU_CULL_OPT_PROFILE       5   /* 1 = bracket every cull-kernel launch with CUDA events (see below) */
+#define DPCU_CULL_OPT_FUSE_LEAF     6   /* 1 (default) = dpcuCullRunWithTree may run the tree's last level   */
+                                        /* inside the cull kernel; 0 = always propagate, then cull           */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
 /* With DPCU_CULL_OPT_PROFILE = 1: device time spent in the cull kernel (K2 only, not the memset /
@@ -252,6 +254,18 @@ int dpcuTreeLocalDevicePointer(dpcuTree *tree, float **deviceMatrices, size_t *n
 int dpcuTreeGetWorld(dpcuTree *tree, size_t first, size_t count, float *hostMatrices);
 int dpcuTreeGetDirtyWorld(dpcuTree *tree, uint32_t *hostWords, size_t nWords);
 int dpcuTreeGetLaunchCount(const dpcuTree *tree, uint64_t *launches);
+
+/* One frame of the reference's update + cull (SceneTree::update -> Tree::compute, then
+ * CullingImpl::cull: dp/sg/xbar/src/SceneTree.cpp:153-170, dp/sg/xbar/culling/src/CullingImpl.cpp:126-144)
+ * in one call: dpcuTreeCompute followed by dpcuCullRun over the tree's world matrices (bound in
+ * place, like dpcuCullBindMatrices) - same results, same dirty-set protocol.  When object i of
+ * the context is bound to the transform of entry i of the tree's LAST level (one drawable per
+ * leaf transform, in tree order; verified on the device and cached), that level is propagated
+ * inside the cull kernel: the leaf world matrices are written out for the renderer and consumed
+ * from shared memory, so they are not read back from HBM (-64 B per object).  Any other binding
+ * runs the two steps back to back. */
+int dpcuCullRunWithTree(dpcuCull *ctx, dpcuTree *tree, dpcuCullResult *const *results,
+                        const float *viewProjections, int nViews, dpcuStream *stream);
 
 /* ===================================================================== synthetic scenes (bench only)
  * On-device replay of pipeline_b200/scenes.py::random_objects: fills packed

@@ -17,7 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE = 1, 2, 3, 4, 5
+OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF = 1, 2, 3, 4, 5, 6
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS = 0, 1, 2, 3
 MAX_VIEWS = 8
 
 _vp = C.c_void_p
@@ -120,6 +121,7 @@ def _declare(L):
         "dpcuCullResultCreate": [_vp, C.POINTER(_vp)],
         "dpcuCullResultDestroy": [_vp],
         "dpcuCullRun": [_vp, C.POINTER(_vp), _f32p, C.c_int, _vp],
+        "dpcuCullRunWithTree": [_vp, _vp, C.POINTER(_vp), _f32p, C.c_int, _vp],
         "dpcuCullResultGetBits": [_vp, _u32p, C.c_size_t],
         "dpcuCullResultGetChangedCount": [_vp, _szp],
         "dpcuCullResultGetChanged": [_vp, _u32p, C.c_size_t, _szp],
@@ -445,6 +447,15 @@ class Cull:
         assert len(vps) == 16 * nv
         arr = (_vp * nv)(*[r.h for r in results])
         check(lib().dpcuCullRun(self.h, arr, vps.ctypes.data_as(_f32p), nv, stream.h if stream else None))
+
+    def run_with_tree(self, tree, results, vps, stream=None):
+        """Tree::compute + cull in one call (the tree's last level fused into the cull kernel when
+        object i is bound to that level's entry i)."""
+        vps = np.ascontiguousarray(vps, dtype=np.float32).reshape(-1)
+        nv = len(results)
+        assert len(vps) == 16 * nv
+        arr = (_vp * nv)(*[r.h for r in results])
+        check(lib().dpcuCullRunWithTree(self.h, tree.h, arr, vps.ctypes.data_as(_f32p), nv, stream.h if stream else None))
 
     def bounding_box(self):
         out = np.zeros(6, dtype=np.float32)

@@ -25,6 +25,7 @@
 #include "cull_stage.cuh"
 #include "cull_views.cuh"
 #include "dpcu_internal.h"
+#include "dpcu_tree.h"
 
 #include <new>
 #include <vector>
@@ -414,6 +415,156 @@ namespace dpcu
     }
     if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
+
+  // ------------------------------------------------------------------------------------------
+  // K1 + K2 fused: the last level of the transform tree is propagated inside the cull kernel
+  // (the leaf world matrices are consumed from on-chip memory while still
+  // being written out for the renderer, which removes their 64 B / object re-read).
+  // Precondition, checked on the device by leafBindingKernel: object i is bound to the node of
+  // the level's entry i (tidx[i] == entries[i].transform), i.e. one drawable per leaf transform
+  // in tree order - the C3 layout.
+  // Each thread computes world = local * world[parent] for its object's node exactly like
+  // treeLevelKernel (same association order, same dirty protocol, Tree.cpp:153-160), stores the
+  // four rows and culls straight out of its registers.
+  struct LeafArgs
+  {
+    uint2 const    *entries;      // {parent, transform} of the fused level, entry i <-> object i
+    float4 const   *local;
+    float4         *world;
+    uint32_t const *dirtyLocal;
+    uint32_t       *dirtyWorld;
+  };
+
+  __device__ __forceinline__ bool leafTestBit( uint32_t const *w, uint32_t i )
+  {
+    return ( w[i >> 5] >> ( i & 31u ) ) & 1u;
+  }
+
+  // One thread per object / leaf node, persistent grid-stride tiles.  The {parent, node} entries
+  // run two tiles ahead and the dirty test one tile ahead of the matrix loads, so every load a
+  // tile issues (8 matrix rows, 2 AABB vectors, the next dirty words, the entry after next) is
+  // independent of the others: one memory latency per tile instead of a chain of three.
+  template <int NV>
+  __global__ void __launch_bounds__( kCullThreads )
+  cullFusedLeafKernel( const __grid_constant__ CullArgs<NV> a, const __grid_constant__ LeafArgs t )
+  {
+    __shared__ float4 sTranspose[kCullThreads / 32][2][128];     // per warp: locals in, worlds out (2 KiB each)
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * kCullThreads;
+    float4 *bufIn = sTranspose[threadIdx.x >> 5][0], *bufOut = sTranspose[threadIdx.x >> 5][1];
+    uint32_t i = blockIdx.x * kCullThreads + threadIdx.x;
+    // prologue of the software pipeline: entry of this tile and of the next, dirty flag of this tile
+    uint2 ent  = make_uint2( 0u, 0u ), entN = make_uint2( 0u, 0u );
+    if ( i < a.n ) ent = __ldg( t.entries + i );
+    if ( i + stride < a.n && i + stride >= i ) entN = __ldg( t.entries + i + stride );
+    bool dirty = i < a.n && ( leafTestBit( t.dirtyWorld, ent.x ) || leafTestBit( t.dirtyLocal, ent.y ) );
+
+    for ( uint32_t tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x, i += stride )
+    {
+      const bool     live = i < a.n;
+      const uint32_t word = i >> 5;
+      uint32_t oldBits = 0;
+      if ( lane < NV && ( i - lane ) < a.n ) oldBits = a.out[lane].bits[word];
+
+      // everything this tile needs from memory, issued together
+      const uint32_t iN = i + stride, iNN = iN + stride;
+      const bool liveN  = iN < a.n && iN >= i;
+      uint2 entNN = make_uint2( 0u, 0u );
+      if ( iNN < a.n && iNN >= iN && liveN ) entNN = __ldg( t.entries + iNN );
+      // parent bits were set by the earlier level launches (never by this kernel); node bits are
+      // set below, but only for nodes of other threads
+      const bool dirtyN = liveN && ( leafTestBit( t.dirtyWorld, entN.x ) || leafTestBit( t.dirtyLocal, entN.y ) );
+      float4 lo = make_float4( 0.f, 0.f, 0.f, 0.f ), ex = lo, w0 = lo, w1 = lo, w2 = lo, w3 = lo;
+      if ( live )
+      {
+        lo = ldStream( a.lowerIdx + i );
+        ex = ldStream( a.extent + i );
+      }
+      // Warp-uniform fast path: a full warp of dirty nodes with consecutive indices (the usual
+      // layout of a level).  The 32 local matrices are 2 KiB contiguous: four coalesced 16-byte
+      // loads per lane bring them in, shared memory (XOR-swizzled, conflict-free both ways) turns
+      // "row j*32+lane" into "my node's four rows", and the same trip backwards turns the world
+      // matrices into four coalesced stores.  Any other warp uses strided per-thread accesses.
+      const uint32_t node0 = __shfl_sync( 0xffffffffu, ent.y, 0 );
+      if ( __all_sync( 0xffffffffu, live && dirty && ent.y == node0 + lane ) )
+      {
+        float4 const *ln = t.local + 4ull * node0;
+        float4       *wn = t.world + 4ull * node0;
+        float4 const *pw = t.world + 4ull * ent.x;
+        const float4 r0 = ldStream( ln + lane ), r1 = ldStream( ln + 32 + lane ), r2 = ldStream( ln + 64 + lane ), r3 = ldStream( ln + 96 + lane );
+        const float4 p0 = __ldg( pw + 0 ), p1 = __ldg( pw + 1 ), p2 = __ldg( pw + 2 ), p3 = __ldg( pw + 3 );
+        const uint32_t oj = lane >> 2, rj = lane & 3u;          // row j*32+lane belongs to node j*8+oj, row rj
+        bufIn[swizzledRow( oj, rj )]      = r0;
+        bufIn[swizzledRow( 8 + oj, rj )]  = r1;
+        bufIn[swizzledRow( 16 + oj, rj )] = r2;
+        bufIn[swizzledRow( 24 + oj, rj )] = r3;
+        __syncwarp();
+        const float4 l0 = bufIn[swizzledRow( lane, 0 )], l1 = bufIn[swizzledRow( lane, 1 )];
+        const float4 l2 = bufIn[swizzledRow( lane, 2 )], l3 = bufIn[swizzledRow( lane, 3 )];
+        w0 = vecMulMat( l0, p0, p1, p2, p3 );                       // Tree.cpp:157, Matmnt.h:1381-1415
+        w1 = vecMulMat( l1, p0, p1, p2, p3 );
+        w2 = vecMulMat( l2, p0, p1, p2, p3 );
+        w3 = vecMulMat( l3, p0, p1, p2, p3 );
+        bufOut[swizzledRow( lane, 0 )] = w0;
+        bufOut[swizzledRow( lane, 1 )] = w1;
+        bufOut[swizzledRow( lane, 2 )] = w2;
+        bufOut[swizzledRow( lane, 3 )] = w3;
+        __syncwarp();
+        wn[lane]      = bufOut[swizzledRow( oj, rj )];
+        wn[32 + lane] = bufOut[swizzledRow( 8 + oj, rj )];
+        wn[64 + lane] = bufOut[swizzledRow( 16 + oj, rj )];
+        wn[96 + lane] = bufOut[swizzledRow( 24 + oj, rj )];
+        if ( lane == 0 ) atomicOr( t.dirtyWorld + ( node0 >> 5 ), 0xffffffffu << ( node0 & 31u ) );          // Tree.cpp:158, 32 nodes
+        if ( lane == 0 && ( node0 & 31u ) ) atomicOr( t.dirtyWorld + ( node0 >> 5 ) + 1, ~( 0xffffffffu << ( node0 & 31u ) ) );
+      }
+      else if ( live )
+      {
+        float4 *wn = t.world + 4ull * ent.y;
+        if ( dirty )
+        {
+          float4 const *ln = t.local + 4ull * ent.y;
+          float4 const *pw = t.world + 4ull * ent.x;
+          const float4 l0 = __ldg( ln + 0 ), l1 = __ldg( ln + 1 ), l2 = __ldg( ln + 2 ), l3 = __ldg( ln + 3 );
+          const float4 p0 = __ldg( pw + 0 ), p1 = __ldg( pw + 1 ), p2 = __ldg( pw + 2 ), p3 = __ldg( pw + 3 );
+          w0 = vecMulMat( l0, p0, p1, p2, p3 );                     // Tree.cpp:157, Matmnt.h:1381-1415
+          w1 = vecMulMat( l1, p0, p1, p2, p3 );
+          w2 = vecMulMat( l2, p0, p1, p2, p3 );
+          w3 = vecMulMat( l3, p0, p1, p2, p3 );
+          wn[0] = w0; wn[1] = w1; wn[2] = w2; wn[3] = w3;
+          atomicOr( t.dirtyWorld + ( ent.y >> 5 ), 1u << ( ent.y & 31u ) );   // Tree.cpp:158
+        }
+        else
+        {
+          w0 = wn[0]; w1 = wn[1]; w2 = wn[2]; w3 = wn[3];
+        }
+      }
+      const Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, w0, w1, w2, w3 );
+      uint32_t myWord = 0;
+      if ( NV == 1 )
+      {
+        myWord = __ballot_sync( 0xffffffffu, obbVisible( obb, a.vp[0][0], a.vp[0][1], a.vp[0][2], a.vp[0][3] ) & live );
+      }
+      else
+      {
+        const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
+        const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
+        const ObbPairs ob = broadcastObb( obb );
+        myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+      }
+      if ( lane < NV && ( i - lane ) < a.n ) storeWord<NV>( a.out[lane], a, word, myWord, oldBits );
+      ent = entN; entN = entNN; dirty = dirtyN;
+    }
+    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+  }
+
+  // counts objects whose transform index is not the node of the level entry with the same index
+  __global__ void leafBindingKernel( float4 const *lowerIdx, uint2 const *entries, uint32_t n, uint32_t *mismatches )
+  {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && __float_as_uint( lowerIdx[i].w ) != entries[i].y;
+    const uint32_t m = __ballot_sync( 0xffffffffu, bad );
+    if ( ( threadIdx.x & 31u ) == 0 && m ) atomicAdd( mismatches, __popc( m ) );
+  }
 #endif
 
 #ifndef DPCU_FMA_VARIANT
@@ -661,7 +812,11 @@ struct dpcuCull
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1;
+  uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
+  dpcuTree    *leafTree = nullptr;       // cached answer of the leaf-binding check of dpcuCullRunWithTree
+  uint64_t     leafTopologyVersion = 0, leafObjectsVersion = 0;
+  bool         leafBound = false;
   uint64_t     launches = 0;
   std::vector<cudaEvent_t> profEvents;   // start/stop pairs of profiled cull-kernel launches
   size_t       profUsed = 0;
@@ -730,7 +885,7 @@ namespace dpcu
   }
 
   template <int NV>
-  static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream )
+  static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf )
   {
     CullArgs<NV> args;
     memset( &args, 0, sizeof args );
@@ -756,8 +911,9 @@ namespace dpcu
     }
     // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
     // issue-bound and the view-sequential packed kernel (cull_views.cuh) is the faster exact form
-    const bool useStaged = !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
-    const bool useViews  = !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
+    const bool useFused  = leaf != nullptr;
+    const bool useStaged = !useFused && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
+    const bool useViews  = !useFused && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
     const size_t stagedSmem = sizeof( WarpRing ) * ( kCullThreads / 32 );
     if ( useStaged ) DPCU_CUDA( cudaFuncSetAttribute( cullStagedKernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( stagedSmem ) ) );
@@ -772,7 +928,8 @@ namespace dpcu
     int perSm = ctx->optCtasPerSm;
     if ( perSm <= 0 )
     {
-      if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
+      if ( useFused ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullFusedLeafKernel<NV>, kCullThreads, 0 );
+      else if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
       else if ( useStaged ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullStagedKernel<NV>, kCullThreads, stagedSmem );
       else if ( useViews ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV>, kCullThreads, 0 );
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullDirectKernel<NV>, kCullThreads, 0 );
@@ -801,7 +958,12 @@ namespace dpcu
       ctx->profUsed += 2;
       DPCU_CUDA( cudaEventRecord( evStart, stream ) );
     }
-    if ( ctx->optFma )
+    if ( useFused )
+    {
+      cullFusedLeafKernel<NV><<<grid, kCullThreads, 0, stream>>>( args, *leaf );
+      DPCU_CUDA( cudaGetLastError() );
+    }
+    else if ( ctx->optFma )
     {
       DPCU_CUDA( launchCullDirectFma<NV>( args, grid, stream ) );
     }
@@ -904,6 +1066,7 @@ extern "C"
       static_cast<float4 *>( ctx->extent.ptr ) + first, static_cast<uint32_t *>( ctx->maxIndex.ptr ) );
     DPCU_CUDA( cudaGetLastError() );
     ++ctx->launches;
+    ++ctx->objectsVersion;
     ctx->maxIndexKnown = false;
     if ( memspace == DPCU_MEM_HOST ) DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
     return DPCU_OK;
@@ -1046,7 +1209,9 @@ extern "C"
     return DPCU_OK;
   }
 
-  int dpcuCullRun( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, dpcuStream *stream )
+}   // extern "C"
+
+  static int runCull( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, cudaStream_t s, dpcu::LeafArgs const *leaf )
   {
     DPCU_REQUIRE( ctx && results && viewProjections, "NULL argument" );
     DPCU_REQUIRE( nViews >= 1 && nViews <= DPCU_MAX_VIEWS, "nViews must be 1..DPCU_MAX_VIEWS" );
@@ -1055,8 +1220,6 @@ extern "C"
       DPCU_REQUIRE( results[v] && results[v]->ctx == ctx, "result does not belong to this context" );
       for ( int u = 0; u < v; ++u ) DPCU_REQUIRE( results[u] != results[v], "results must be distinct" );
     }
-    dpcu::DeviceGuard guard( ctx->device );
-    cudaStream_t s = stream ? stream->stream : ctx->stream;
     if ( s != ctx->stream )
     {
       // uploads were submitted on the context stream: order this run after them on the device
@@ -1099,14 +1262,14 @@ extern "C"
     int rc = DPCU_OK;
     switch ( nViews )
     {
-      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s ); break;
-      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s ); break;
-      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s ); break;
-      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s ); break;
-      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s ); break;
-      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s ); break;
-      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s ); break;
-      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s ); break;
+      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf ); break;
+      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf ); break;
+      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf ); break;
+      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf ); break;
+      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf ); break;
+      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf ); break;
+      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf ); break;
+      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf ); break;
     }
     DPCU_TRY( rc );
     if ( ctx->optChanged )
@@ -1130,6 +1293,72 @@ extern "C"
     for ( int v = 0; v < nViews; ++v ) DPCU_CUDA( results[v]->done.record( s ) );
     if ( s != ctx->stream ) DPCU_CUDA( ctx->lastRun.record( s ) );
     return DPCU_OK;
+  }
+
+
+extern "C"
+{
+  int dpcuCullRun( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, dpcuStream *stream )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    dpcu::DeviceGuard guard( ctx->device );
+    return runCull( ctx, results, viewProjections, nViews, stream ? stream->stream : ctx->stream, nullptr );
+  }
+
+  int dpcuCullRunWithTree( dpcuCull *ctx, dpcuTree *tree, dpcuCullResult *const *results, const float *viewProjections, int nViews,
+                           dpcuStream *stream )
+  {
+    DPCU_REQUIRE( ctx && tree, "NULL argument" );
+    DPCU_REQUIRE( tree->device == ctx->device, "tree and culling context live on different devices" );
+    DPCU_REQUIRE( tree->numNodes >= 1, "no topology set" );
+    dpcu::DeviceGuard guard( ctx->device );
+    cudaStream_t s = stream ? stream->stream : ctx->stream;
+    // the culler reads the tree's world matrices in place
+    ctx->boundMats = static_cast<float const *>( tree->world.ptr );
+    ctx->nMats     = tree->numNodes;
+    const size_t levels = tree->levelOffsets.empty() ? 0 : tree->levelOffsets.size() - 1;
+    // can the last level run inside the cull kernel?  object i <-> entry i of that level
+    bool fuse = false;
+    size_t lastFirst = 0;
+    if ( levels >= 1 && ctx->n && ctx->optFuseLeaf && !ctx->optFma )
+    {
+      lastFirst = tree->levelOffsets[levels - 1];
+      const size_t lastCount = tree->levelOffsets[levels] - lastFirst;
+      if ( lastCount == ctx->n )
+      {
+        if ( ctx->leafTree != tree || ctx->leafTopologyVersion != tree->topologyVersion || ctx->leafObjectsVersion != ctx->objectsVersion )
+        {
+          DPCU_TRY( ctx->scratch.reserve( 256, false, ctx->stream ) );
+          DPCU_CUDA( cudaMemsetAsync( ctx->scratch.ptr, 0, 4, ctx->stream ) );
+          dpcu::leafBindingKernel<<<unsigned( dpcu::divUp( ctx->n, 256 ) ), 256, 0, ctx->stream>>>(
+            static_cast<float4 const *>( ctx->lowerIdx.ptr ), static_cast<uint2 const *>( tree->entries.ptr ) + lastFirst,
+            uint32_t( ctx->n ), static_cast<uint32_t *>( ctx->scratch.ptr ) );
+          DPCU_CUDA( cudaGetLastError() );
+          ++ctx->launches;
+          uint32_t mismatches = 0;
+          DPCU_CUDA( cudaMemcpyAsync( &mismatches, ctx->scratch.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+          DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
+          ctx->leafTree = tree;
+          ctx->leafTopologyVersion = tree->topologyVersion;
+          ctx->leafObjectsVersion  = ctx->objectsVersion;
+          ctx->leafBound = mismatches == 0;
+        }
+        fuse = ctx->leafBound;
+      }
+    }
+    DPCU_TRY( dpcu::treeBeginCompute( tree, s ) );
+    DPCU_TRY( dpcu::treeComputeLevels( tree, s, 0, fuse ? levels - 1 : levels ) );
+    dpcu::LeafArgs leaf;
+    leaf.entries    = static_cast<uint2 const *>( tree->entries.ptr ) + lastFirst;
+    leaf.local      = static_cast<float4 const *>( tree->local.ptr );
+    leaf.world      = static_cast<float4 *>( tree->world.ptr );
+    leaf.dirtyLocal = static_cast<uint32_t const *>( tree->dirtyLocal.ptr );
+    leaf.dirtyWorld = static_cast<uint32_t *>( tree->dirtyWorld.ptr );
+    int rc = runCull( ctx, results, viewProjections, nViews, s, fuse ? &leaf : nullptr );
+    if ( fuse && rc == DPCU_OK ) ++tree->launches;        // the fused kernel is the tree's last level too
+    // close the tree's compute even if the cull failed, so its dirty state stays consistent
+    int rc2 = dpcu::treeEndCompute( tree, s );
+    return rc != DPCU_OK ? rc : rc2;
   }
 
   int dpcuCullResultGetBits( dpcuCullResult *r, uint32_t *hostWords, size_t nWords )
@@ -1289,6 +1518,7 @@ extern "C"
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;
       case DPCU_CULL_OPT_PROFILE:      ctx->optProfile = value ? 1 : 0; break;
+      case DPCU_CULL_OPT_FUSE_LEAF:    ctx->optFuseLeaf = value ? 1 : 0; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -1304,6 +1534,7 @@ extern "C"
       case DPCU_CULL_OPT_CHANGED_LIST: *value = ctx->optChanged; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  *value = ctx->optCtasPerSm; break;
       case DPCU_CULL_OPT_PROFILE:      *value = ctx->optProfile; break;
+      case DPCU_CULL_OPT_FUSE_LEAF:    *value = ctx->optFuseLeaf; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
     return DPCU_OK;

@@ -12,6 +12,7 @@
 // share through L1/L2.  Compiled with -fmad=false.
 #include "cull_math.cuh"
 #include "dpcu_internal.h"
+#include "dpcu_tree.h"
 
 #include <new>
 #include <vector>
@@ -77,18 +78,49 @@ namespace dpcu
   }
 }
 
-struct dpcuTree
+
+namespace dpcu
 {
-  int          device = 0;
-  cudaStream_t stream = nullptr;
-  dpcu::DeviceArray local, world, entries, dirtyLocal, dirtyWorld, scratch;
-  size_t       numNodes = 0;
-  size_t       numEntries = 0;
-  std::vector<uint32_t> levelOffsets;
-  uint64_t     launches = 0;
-  dpcu::StreamFence done;        // last compute submitted
-  dpcu::StreamFence uploads;
-};
+  // Tree::compute in three steps so that the culling layer can run the last level inside its own
+  // kernel (dpcuCullRunWithTree): begin = ordering + drop the previous published dirty set,
+  // levels [first, last), end = clear the local dirty bits (Tree.cpp:163) + fence.
+  int treeBeginCompute( dpcuTree *t, cudaStream_t s )
+  {
+    if ( s != t->stream )
+    {
+      DPCU_CUDA( t->uploads.record( t->stream ) );      // topology / local-matrix updates ran on the tree's stream
+      DPCU_CUDA( t->uploads.orderBefore( s ) );
+    }
+    DPCU_CUDA( t->done.orderBefore( s ) );
+    size_t words = divUp( t->numNodes, 32 );
+    // the previous compute's published set is dropped now (the reference clears it right after notifying, Tree.cpp:163-164)
+    DPCU_CUDA( cudaMemsetAsync( t->dirtyWorld.ptr, 0, words * 4, s ) );
+    return DPCU_OK;
+  }
+
+  int treeComputeLevels( dpcuTree *t, cudaStream_t s, size_t firstLevel, size_t lastLevel )
+  {
+    for ( size_t l = firstLevel; l < lastLevel; ++l )
+    {
+      uint32_t first = t->levelOffsets[l], count = t->levelOffsets[l + 1] - first;
+      if ( !count ) continue;
+      treeLevelKernel<<<unsigned( divUp( size_t( count ) * 4, 256 ) ), 256, 0, s>>>(
+        static_cast<uint2 const *>( t->entries.ptr ) + first, count, static_cast<float4 const *>( t->local.ptr ),
+        static_cast<float4 *>( t->world.ptr ), static_cast<uint32_t const *>( t->dirtyLocal.ptr ), static_cast<uint32_t *>( t->dirtyWorld.ptr ) );
+      DPCU_CUDA( cudaGetLastError() );
+      ++t->launches;
+    }
+    return DPCU_OK;
+  }
+
+  int treeEndCompute( dpcuTree *t, cudaStream_t s )
+  {
+    size_t words = divUp( t->numNodes, 32 );
+    DPCU_CUDA( cudaMemsetAsync( t->dirtyLocal.ptr, 0, words * 4, s ) );   // Tree.cpp:163
+    DPCU_CUDA( t->done.record( s ) );
+    return DPCU_OK;
+  }
+}
 
 extern "C"
 {
@@ -171,6 +203,7 @@ extern "C"
     DPCU_CUDA( cudaStreamSynchronize( s ) );
     t->numNodes = numNodes;
     t->numEntries = numEntries;
+    ++t->topologyVersion;
     t->levelOffsets.assign( levelOffsets, levelOffsets + ( numLevels ? numLevels + 1 : 0 ) );
     return DPCU_OK;
   }
@@ -235,28 +268,10 @@ extern "C"
     DPCU_REQUIRE( t->numNodes >= 1, "no topology set" );
     dpcu::DeviceGuard guard( t->device );
     cudaStream_t s = stream ? stream->stream : t->stream;
-    if ( s != t->stream )
-    {
-      DPCU_CUDA( t->uploads.record( t->stream ) );      // topology / local-matrix updates ran on the tree's stream
-      DPCU_CUDA( t->uploads.orderBefore( s ) );
-    }
-    DPCU_CUDA( t->done.orderBefore( s ) );
-    size_t words = dpcu::divUp( t->numNodes, 32 );
-    // the previous compute's published set is dropped now (the reference clears it right after notifying, Tree.cpp:163-164)
-    DPCU_CUDA( cudaMemsetAsync( t->dirtyWorld.ptr, 0, words * 4, s ) );
     size_t levels = t->levelOffsets.empty() ? 0 : t->levelOffsets.size() - 1;
-    for ( size_t l = 0; l < levels; ++l )
-    {
-      uint32_t first = t->levelOffsets[l], count = t->levelOffsets[l + 1] - first;
-      if ( !count ) continue;
-      dpcu::treeLevelKernel<<<unsigned( dpcu::divUp( size_t( count ) * 4, 256 ) ), 256, 0, s>>>(
-        static_cast<uint2 const *>( t->entries.ptr ) + first, count, static_cast<float4 const *>( t->local.ptr ),
-        static_cast<float4 *>( t->world.ptr ), static_cast<uint32_t const *>( t->dirtyLocal.ptr ), static_cast<uint32_t *>( t->dirtyWorld.ptr ) );
-      DPCU_CUDA( cudaGetLastError() );
-      ++t->launches;
-    }
-    DPCU_CUDA( cudaMemsetAsync( t->dirtyLocal.ptr, 0, words * 4, s ) );   // Tree.cpp:163
-    DPCU_CUDA( t->done.record( s ) );
+    DPCU_TRY( dpcu::treeBeginCompute( t, s ) );
+    DPCU_TRY( dpcu::treeComputeLevels( t, s, 0, levels ) );
+    DPCU_TRY( dpcu::treeEndCompute( t, s ) );
     return DPCU_OK;
   }
 

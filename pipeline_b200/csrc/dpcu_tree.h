@@ -1,0 +1,28 @@
+// Internal view of the transform layer (dpcu_tree.cu) for the culling layer's fused
+// propagate-and-cull path.  Not part of the C ABI.
+#pragma once
+
+#include "dpcu_internal.h"
+
+#include <vector>
+
+struct dpcuTree
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  dpcu::DeviceArray local, world, entries, dirtyLocal, dirtyWorld, scratch;
+  size_t       numNodes = 0;
+  size_t       numEntries = 0;
+  std::vector<uint32_t> levelOffsets;
+  uint64_t     launches = 0;
+  uint64_t     topologyVersion = 0;   // bumped by dpcuTreeSetTopology (cached leaf bindings of cull contexts go stale)
+  dpcu::StreamFence done;        // last compute submitted
+  dpcu::StreamFence uploads;
+};
+
+namespace dpcu
+{
+  int treeBeginCompute( dpcuTree *t, cudaStream_t s );
+  int treeComputeLevels( dpcuTree *t, cudaStream_t s, size_t firstLevel, size_t lastLevel );
+  int treeEndCompute( dpcuTree *t, cudaStream_t s );
+}

@@ -444,6 +444,72 @@ def test_tree_feeds_cull_zero_copy(capi, port):
     r.close(), ctx.close(), t.close()
 
 
+@pytest.mark.parametrize("nv", [1, 3])
+@pytest.mark.parametrize("binding", ["leaf-order", "permuted", "fusion-off"])
+def test_run_with_tree_fused_leaf_level(capi, port, nv, binding):
+    """dpcuCullRunWithTree == Tree::compute followed by cull, for the fused path (object i bound to
+    leaf entry i), for a binding that cannot be fused, and with fusion switched off: world
+    matrices, published dirty set, visibility bits and changed lists all equal the oracle's, over
+    frames that dirty everything / a few scattered nodes / nothing."""
+    levels = (5, 35, 315, 2835)                      # ragged: leaf count is not a multiple of 32
+    entries, offsets, n_nodes = scenes.hierarchy_topology(levels)
+    n = levels[-1]
+    first_leaf = n_nodes - n
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=0)
+    lower4, extent4, upper4, _, _ = cases.random_case(n)
+    tidx = np.arange(first_leaf, n_nodes, dtype=np.uint32)
+    if binding == "permuted":
+        tidx = tidx[::-1].copy()
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    t.set_locals(0, local)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    if binding == "fusion-off":
+        ctx.set_option(capi.OPT_FUSE_LEAF, 0)
+    res = [ctx.result_create() for _ in range(nv)]
+    view = scenes.make_look_at((0, 0, 150), (0, 0, 0), (0, 1, 0))
+    vps = np.stack([scenes.mat_mul(view, scenes.make_perspective(fov, 1.3, 1.0, 500.0)) for fov in (40.0, 15.0, 75.0)][:nv])
+    world = np.zeros_like(local)
+    world[0] = np.eye(4, dtype=np.float32)
+    nw = (n_nodes + 31) // 32
+    dl = np.zeros(nw, np.uint32)
+    dl[:] = 0xFFFFFFFF                               # new nodes start dirty (Tree.cpp:63)
+    state = [port.result_resize(np.zeros(0, np.uint32), 0, n) for _ in range(nv)]
+    rng = np.random.RandomState(5)
+    launches_before = t.launches()
+    for frame in range(4):
+        if frame == 1:                               # a few scattered nodes on every level
+            idx = np.unique(np.concatenate([rng.randint(1, n_nodes, size=40), [1, first_leaf, n_nodes - 1]])).astype(np.uint32)
+            local[idx] = scenes.hierarchy_locals(scenes.SEED_C3 + 9, 1, len(idx), frame=7)
+            t.update_locals(idx, local[idx])
+            for i in idx:
+                dl[i >> 5] |= np.uint32(1 << (int(i) & 31))
+        elif frame == 2:                             # nothing dirty: world must stay, published set empty
+            pass
+        elif frame == 3:                             # leaves only
+            local[first_leaf:] = scenes.hierarchy_locals(scenes.SEED_C3 + 3, first_leaf, n, frame=2)
+            t.set_locals(first_leaf, local[first_leaf:])
+            for i in range(first_leaf, n_nodes):
+                dl[i >> 5] |= np.uint32(1 << (i & 31))
+        ctx.run_with_tree(t, res, vps)
+        dw = np.zeros(nw, np.uint32)
+        port.tree_compute(local, world, entries, offsets, dl, dw)
+        assert np.array_equal(t.world().view(np.uint32), world.view(np.uint32)), (frame, "world matrices")
+        assert np.array_equal(t.dirty_world()[:nw], dw), (frame, "published dirty set")
+        for v in range(nv):
+            want = port.cull_bits(lower4, extent4, tidx, world.reshape(-1), vps[v])
+            assert np.array_equal(res[v].bits(), want), (frame, v)
+            assert np.array_equal(res[v].changed(), port.update_changed(want, state[v], n)), (frame, v)
+    # launches: 4 levels per frame unfused, 3 level kernels + the fused cull kernel (counted once) when fused
+    assert t.launches() - launches_before >= 4 * 4
+    for r in res:
+        r.close()
+    ctx.close(), t.close()
+
+
 # ------------------------------------------------------------------ dp/cuda layer
 def test_buffers_streams_events(capi):
     s = capi.Stream()
