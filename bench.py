@@ -313,10 +313,16 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_option(capi.OPT_PROFILE, 1)
     results = [ctx.result_create() for _ in range(views)]
 
-    # ---------------- multi-GPU: the bitset all-gather is the cull kernel's epilogue (NVLink peer stores)
+    # ---------------- multi-GPU: the bitset all-gather is the cull kernel's epilogue (NVLink peer stores).
+    # The sharded cull itself has no exchange step; the all-gather exists for consumers
+    # that need the full bitset on every GPU.  --gather also (default): the headline step is the cull
+    # alone and the same step WITH the fused all-gather is measured afterwards and reported under
+    # "also"; --gather fused: the all-gather is part of the headline step; --gather none: never.
     gather = "none"
     full_bits, peer_ptrs = [], []
-    if world > 1 and args.gather == "fused":
+
+    def enable_gather():
+        nonlocal gather
         from pipeline_b200 import sharding
         try:
             words_total = sharding.total_words(n_total)
@@ -328,11 +334,27 @@ def run_ours(args, rank, world, local_rank):
                 ptrs = [fb.ptr if r == rank else capi.ipc_open(handles[r]) for r in range(world)]
                 peer_ptrs.append(ptrs)
                 results[v].set_peer_bits(ptrs, sharding.word_offset(first))
-            gather = "fused: every rank's cull kernel stores its words into all %d full bitsets (cudaIpc peer pointers)" % world
+            gather = ("fused: every rank's cull kernel (cullLinesKernel) stores its finished 128-byte lines into all %d full "
+                      "bitsets (cudaIpc peer pointers, NVLink stores)" % world)
+            return True
         except Exception as e:                      # noqa: BLE001 - report, do not hide
             gather = "none (peer mapping failed: %s)" % e
             for v in range(views):
                 results[v].set_peer_bits([], 0)
+            return False
+
+    def verify_gather():
+        from pipeline_b200 import sharding
+        barrier()
+        local = torch.from_numpy(results[0].bits().view(np.int32)).cuda()
+        parts = sharding.allgather_words(dist, local, n_words)
+        want = torch.cat(parts).cpu().numpy().view(np.uint32)
+        got = np.zeros(sharding.total_words(n_total), np.uint32)
+        full_bits[0].download(got)
+        return bool(np.array_equal(got, want[:len(got)]))
+
+    if world > 1 and args.gather == "fused":
+        enable_gather()
 
     if views > 1:
         # six static faces plus a slowly translating eye so that the changed lists are not empty
@@ -448,14 +470,7 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- multi-GPU: check the fused all-gather against the library collective (untimed)
     gather_ok = None
     if full_bits:
-        from pipeline_b200 import sharding
-        barrier()
-        local = torch.from_numpy(results[0].bits().view(np.int32)).cuda()
-        parts = sharding.allgather_words(dist, local, n_words)
-        want = torch.cat(parts).cpu().numpy().view(np.uint32)
-        got = np.zeros(sharding.total_words(n_total), np.uint32)
-        full_bits[0].download(got)
-        gather_ok = bool(np.array_equal(got, want[:len(got)]))
+        gather_ok = verify_gather()
 
     # ---------------- roofline of the dominant kernel (K2, the cull kernel)
     peak, peak_src = measured_peak()
@@ -467,11 +482,12 @@ def run_ours(args, rank, world, local_rank):
         kernel_name = "cullFusedLeafKernel<%d>" % views
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = alg_bytes / (k_avg_ms / 1000.0) / 1e9
-    traffic = None
+    traffic = None                                       # dram bytes of the same kernel / workload from the committed ncu capture
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_cull_kernel_summary.json")))
         for p in prof.get("captures", []):
-            if p.get("workload") == args.workload and p.get("objects") == n_per and p.get("views") == views:
+            if (p.get("workload") == args.workload and p.get("objects") == n_per and p.get("views") == views
+                    and kernel_name.split("<")[0] in p.get("kernel", "")):
                 traffic = p["dram_bytes_read"] + p["dram_bytes_write"]
     except Exception:
         pass
@@ -485,6 +501,66 @@ def run_ours(args, rank, world, local_rank):
         roofline["step_algorithmic_bytes"] = alg_upper + alg_bytes       # 3.05 GB: the fused figure of SURVEY.md 8d
         roofline["step_achieved"] = (alg_upper + alg_bytes) / (ms_per_step / 1000.0) / 1e9
         roofline["step_frac"] = roofline["step_achieved"] / peak
+
+    also = {}
+    # ---------------- the same step with the bitset all-gather fused into the cull kernel (N > 1)
+    if world > 1 and args.gather == "also" and tree is None:
+        if enable_gather():
+            for f in range(3):
+                step(f)
+            stream.sync()
+            ctx.kernel_time()
+            barrier()
+            e0.record(stream)
+            for f in range(K):
+                step(W + f)
+            e1.record(stream)
+            stream.sync()
+            ms_g = e0.elapsed_ms(e1)
+            t = torch.tensor([ms_g], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_g = float(t.item()) / K
+            kg_ms, kg_n = ctx.kernel_time()
+            ok = verify_gather()
+            also["with_bitset_allgather"] = {
+                "ms_per_step": ms_g, "objects_per_s": n_total / (ms_g / 1000.0), "kernel": "cullLinesKernel<%d>" % views,
+                "avg_launch_ms": kg_ms / max(kg_n, 1), "how": gather, "verified_against_nccl_all_gather": ok,
+                "nvlink_bytes_out_per_gpu_per_step": (world - 1) * n_words * 4 * views}
+            for v in range(views):
+                results[v].set_peer_bits([], 0)
+        gather = "not part of the headline step (no data-path collective); measured separately under also.with_bitset_allgather"
+        gather_ok = None
+
+    # ---------------- the same resident scene against six cube-map frusta in one pass (BASELINE config 4)
+    if args.workload == "c4-single" and not args.no_also:
+        res6 = [ctx.result_create() for _ in range(6)]
+        cams6 = [np.ascontiguousarray(scenes.cube_map_cameras((3.0 * f, 0.0, 0.0)), np.float32) for f in range(W + 10)]
+        for f in range(W):
+            ctx.run(res6, cams6[f], stream)
+        stream.sync()
+        ctx.kernel_time()
+        barrier()
+        e0.record(stream)
+        for f in range(10):
+            ctx.run(res6, cams6[W + f], stream)
+        e1.record(stream)
+        stream.sync()
+        ms6 = e0.elapsed_ms(e1)
+        if dist is not None:
+            t = torch.tensor([ms6], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms6 = float(t.item())
+        ms6 /= 10
+        k6_ms, k6_n = ctx.kernel_time()
+        alg6 = n_per * (96.0 + 0.25 * 6)
+        also["c4_six_views"] = {
+            "ms_per_step": ms6, "objects_per_s": n_total / (ms6 / 1000.0), "object_views_per_s": 6 * n_total / (ms6 / 1000.0),
+            "kernel": "cullViewsKernel<6>", "avg_launch_ms": k6_ms / max(k6_n, 1),
+            "achieved_GBps": alg6 / (k6_ms / max(k6_n, 1) / 1000.0) / 1e9, "frac_of_hbm_peak": alg6 / (k6_ms / max(k6_n, 1) / 1000.0) / 1e9 / peak,
+            "bound": "issue (72 compares + 56 packed mul/add per object and view; see DESIGN.md section 3)",
+            "changed_per_step_last": [r.changed_count() for r in res6]}
+        for r in res6:
+            r.close()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -506,6 +582,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
     }
+    if also:
+        line["also"] = also
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single_core(args.workload, seed)
     if rank == 0:
@@ -526,8 +604,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4-single", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "none"],
-                    help="N>1: all-gather the bitsets through peer stores in the cull kernel's epilogue (default) or not at all")
+    ap.add_argument("--no-also", action="store_true", help="skip the six-view pass over the same scene")
+    ap.add_argument("--gather", default="also", choices=["also", "fused", "none"],
+                    help="N>1: bitset all-gather through peer stores in the cull kernel's epilogue: measured next to the "
+                         "headline step (also, default), inside it (fused), or not at all (none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

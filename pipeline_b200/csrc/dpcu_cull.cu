@@ -168,10 +168,6 @@ namespace dpcu
         {
           ViewOut const &o = a.out[v];
           o.bits[word] = nw;
-          for ( uint32_t p = 0; p < a.nPeers; ++p )
-          {
-            if ( o.peer[p] ) o.peer[p][a.peerWordOffset + word] = nw;
-          }
           if ( a.buildChanged )
           {
             const uint32_t c = oldBits[v] ^ nw;
@@ -234,10 +230,6 @@ namespace dpcu
       {
         ViewOut const &o = a.out[lane];
         o.bits[word] = myWord;
-        for ( uint32_t p = 0; p < a.nPeers; ++p )
-        {
-          if ( o.peer[p] ) o.peer[p][a.peerWordOffset + word] = myWord;
-        }
         if ( a.buildChanged )
         {
           const uint32_t c = oldBits ^ myWord;
@@ -286,10 +278,6 @@ namespace dpcu
   __device__ __forceinline__ void storeWord( ViewOut const &o, CullArgs<NV> const &a, uint32_t word, uint32_t nw, uint32_t old )
   {
     o.bits[word] = nw;
-    for ( uint32_t p = 0; p < a.nPeers; ++p )
-    {
-      if ( o.peer[p] ) o.peer[p][a.peerWordOffset + word] = nw;
-    }
     if ( a.buildChanged )
     {
       const uint32_t c = old ^ nw;
@@ -412,6 +400,102 @@ namespace dpcu
       if ( lane < NV ) storeWord<NV>( a.out[lane], a, tile0, myWord, old0 );
       tile0 = tile1; tile1 = tile2;
       old0 = old1;
+    }
+    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // K2, line-granular variant - the multi-GPU form.  A warp owns 1024 consecutive objects (32
+  // words = one 128-byte line of each bitset) and walks them in 32 steps of 32 objects; lane w
+  // keeps the ballot of step w, so at the end lane l holds word l of the line.  Previous bits are
+  // read and new bits / flipped bits are written as whole lines, the changed-count goes to the
+  // segment counter once per line, and - the point of this form - the bitset all-gather of
+  // SURVEY.md 8e is the same coalesced 128-byte store repeated into every peer's full bitset
+  // over NVLink: whole lines on the wire, no barrier, no shared memory, no separate collective.
+  // (Per-word 4-byte peer stores from the direct kernel were measured at 1.87 ms per 64 Mi-object
+  // step on 8 GPUs; a shared-memory hand-over with two CTA barriers at 1.21 ms; the cull alone 0.98 ms.)
+  template <int NV>
+  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : 2 )
+  cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
+  {
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t nWords = ( a.n + 31u ) >> 5, nLines = ( nWords + 31u ) >> 5;
+    const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
+    for ( uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 ); line < nLines; line += nWarps )
+    {
+      const uint32_t word0 = line << 5, myWord = word0 + lane;
+      const bool     wordLive = myWord < nWords;
+      uint32_t old[NV], acc[NV];
+#pragma unroll
+      for ( int v = 0; v < NV; ++v )
+      {
+        old[v] = wordLive ? a.out[v].bits[myWord] : 0u;
+        acc[v] = 0u;
+      }
+      const uint32_t steps = min( 32u, nWords - word0 );
+#pragma unroll 1      // measured: one step in flight at 48 warps per SM beats unroll 2 / 4 at lower occupancy
+      for ( uint32_t w = 0; w < steps; ++w )
+      {
+        const uint32_t i    = ( ( word0 + w ) << 5 ) + lane;
+        const bool     live = i < a.n;
+        Obb obb;
+        obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );
+        if ( live )
+        {
+          const float4 lo = ldStream( a.lowerIdx + i );
+          const float4 ex = ldStream( a.extent + i );
+          float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
+          const float4 m0 = __ldg( m + 0 );
+          const float4 m1 = __ldg( m + 1 );
+          const float4 m2 = __ldg( m + 2 );
+          const float4 m3 = __ldg( m + 3 );
+          obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+        }
+        if ( NV == 1 )
+        {
+          const uint32_t b = __ballot_sync( 0xffffffffu, obbVisible( obb, a.vp[0][0], a.vp[0][1], a.vp[0][2], a.vp[0][3] ) & live );
+          if ( lane == w ) acc[0] = b;
+        }
+        else
+        {
+          const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
+          const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
+          const ObbPairs ob = broadcastObb( obb );
+          const uint32_t perView = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+#pragma unroll
+          for ( int v = 0; v < NV; ++v )
+          {
+            const uint32_t b = __shfl_sync( 0xffffffffu, perView, v );     // lane v held view v's word
+            if ( lane == w ) acc[v] = b;
+          }
+        }
+      }
+#pragma unroll
+      for ( int v = 0; v < NV; ++v )
+      {
+        ViewOut const &o = a.out[v];
+        uint32_t flips = 0;
+        if ( wordLive )
+        {
+          o.bits[myWord] = acc[v];
+          for ( uint32_t p = 0; p < a.nPeers; ++p )
+          {
+            if ( o.peer[p] ) o.peer[p][a.peerWordOffset + myWord] = acc[v];
+          }
+          if ( a.buildChanged )
+          {
+            const uint32_t c = old[v] ^ acc[v];
+            o.chg[myWord] = c;
+            flips = __popc( c );
+          }
+        }
+        if ( a.buildChanged )
+        {
+#pragma unroll
+          for ( int d = 16; d > 0; d >>= 1 ) flips += __shfl_xor_sync( 0xffffffffu, flips, d );
+          if ( lane == 0 && flips ) atomicAdd( o.seg + ( word0 >> ( kSegObjectsLog2 - 5 ) ), flips );
+        }
+      }
     }
     if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
@@ -911,9 +995,13 @@ namespace dpcu
     }
     // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
     // issue-bound and the view-sequential packed kernel (cull_views.cuh) is the faster exact form
+    const bool peers     = args.nPeers > 0;
+    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES );
+    if ( peers && ( ctx->optFma || leaf ) )
+      return fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: peer bitsets are served by the line-granular kernel only (not the FMA or fused-leaf forms)" );
     const bool useFused  = leaf != nullptr;
-    const bool useStaged = !useFused && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
-    const bool useViews  = !useFused && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
+    const bool useStaged = !useFused && !useLines && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
+    const bool useViews  = !useFused && !useLines && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
     const size_t stagedSmem = sizeof( WarpRing ) * ( kCullThreads / 32 );
     if ( useStaged ) DPCU_CUDA( cudaFuncSetAttribute( cullStagedKernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( stagedSmem ) ) );
@@ -929,6 +1017,7 @@ namespace dpcu
     if ( perSm <= 0 )
     {
       if ( useFused ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullFusedLeafKernel<NV>, kCullThreads, 0 );
+      else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV>, kCullThreads, 0 );
       else if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
       else if ( useStaged ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullStagedKernel<NV>, kCullThreads, stagedSmem );
       else if ( useViews ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV>, kCullThreads, 0 );
@@ -961,6 +1050,14 @@ namespace dpcu
     if ( useFused )
     {
       cullFusedLeafKernel<NV><<<grid, kCullThreads, 0, stream>>>( args, *leaf );
+      DPCU_CUDA( cudaGetLastError() );
+    }
+    else if ( useLines )
+    {
+      const uint32_t nLines = uint32_t( divUp( divUp( ctx->n, 32 ), 32 ) );
+      const uint32_t ctasForLines = uint32_t( divUp( nLines, kCullThreads / 32 ) );
+      if ( uint32_t( grid ) > ctasForLines ) grid = int( ctasForLines );
+      cullLinesKernel<NV><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
     }
     else if ( ctx->optFma )
@@ -1513,7 +1610,7 @@ extern "C"
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     switch ( option )
     {
-      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 3, "kernel must be 0..3" ); ctx->optKernel = value; break;
+      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 4, "kernel must be 0..4" ); ctx->optKernel = value; break;
       case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;

@@ -202,7 +202,7 @@ def test_multi_view_equals_single_views(capi, port):
 
 
 # ------------------------------------------------------------------ both exact kernel forms, 1..8 views
-KERNELS = {"direct": 1, "staged": 2, "views": 3}
+KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4}
 
 
 def _views_for(nv, extra=()):
@@ -508,6 +508,52 @@ def test_run_with_tree_fused_leaf_level(capi, port, nv, binding):
     for r in res:
         r.close()
     ctx.close(), t.close()
+
+
+@pytest.mark.parametrize("nv", [1, 3])
+def test_peer_bitset_gather_in_kernel_epilogue(capi, port, nv):
+    """The multi-GPU all-gather of the bitsets is the cull kernel's epilogue: every
+    shard stores its finished 128-byte lines into the full bitset of every peer.  Emulated here
+    on one device with two shards and two 'peer' buffers: both full bitsets must equal the
+    oracle's bitset of the whole scene, for the direct (1 view) and the view-sequential kernel."""
+    n = 3 * 1024 * 7 + 531                              # ragged: the last shard ends inside a line
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C4)
+    split = 1024 * 9                                     # shard starts are multiples of 1024 objects
+    vps = _views_for(nv)
+    words = (n + 31) // 32
+    full = [[capi.Buffer(((words + 31) // 32) * 128) for _ in range(nv)] for _ in range(2)]
+    for bufs in full:
+        for b in bufs:
+            b.fill(0)
+    shards = []
+    for rank, (lo, hi) in enumerate(((0, split), (split, n))):
+        ctx = capi.Cull(0)
+        ctx.set_objects(lower4[lo:hi], extent4[lo:hi], (tidx[lo:hi] - np.uint32(lo)).astype(np.uint32))
+        ctx.set_matrices(mats[lo:hi].reshape(-1))
+        res = [ctx.result_create() for _ in range(nv)]
+        for v in range(nv):
+            res[v].set_peer_bits([full[0][v].ptr, full[1][v].ptr], lo // 32)
+        shards.append((ctx, res, lo, hi))
+    for frame in range(2):
+        use = vps if frame == 0 else vps[::-1].copy()
+        for ctx, res, lo, hi in shards:
+            ctx.run(res, use)
+        capi.device_sync()
+        for v in range(nv):
+            want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), use[v])
+            for peer in range(2):
+                got = np.zeros(((words + 31) // 32) * 32, np.uint32)
+                full[peer][v].download(got)
+                assert np.array_equal(got[:words], want), (frame, v, peer)
+            # the shard-local results are unaffected by the gather
+            for ctx, res, lo, hi in shards:
+                local = res[v].bits()
+                assert np.array_equal(local, port.cull_bits(lower4[lo:hi], extent4[lo:hi], (tidx[lo:hi] - np.uint32(lo)).astype(np.uint32),
+                                                            mats[lo:hi].reshape(-1), use[v]))
+    for ctx, res, lo, hi in shards:
+        for r in res:
+            r.close()
+        ctx.close()
 
 
 # ------------------------------------------------------------------ dp/cuda layer

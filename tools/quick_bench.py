@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--fma", type=int, default=0)
     ap.add_argument("--changed", type=int, default=1)
     ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
+    ap.add_argument("--flush", type=int, default=0, help="1: write 256 MiB between iterations (cold L2)")
     a = ap.parse_args()
     n = a.n
     lo, ex, mt = capi.Buffer(n * 16), capi.Buffer(n * 16), capi.Buffer(n * 64)
@@ -48,13 +49,20 @@ def main():
         ctx.run(res, cam[f], s)
     s.sync()
     times = []
+    ctx.set_option(capi.OPT_PROFILE, 1)
+    ctx.kernel_time()
+    flush = capi.Buffer(256 << 20) if a.flush else None
     for f in range(a.iters):
+        if flush is not None:
+            flush.fill(f & 0xFF)
+            capi.device_sync()
         e0.record(s)
         ctx.run(res, cam[3 + f], s)
         e1.record(s)
         s.sync()
         times.append(e0.elapsed_ms(e1))
     t = np.median(times)
+    k_ms, k_n = ctx.kernel_time()
     nchg = sum(r.changed_count() for r in res) if a.changed else 0
     bytes_alg = n * (96 + 0.25 * a.views) + 4 * nchg
     import zlib
@@ -62,8 +70,8 @@ def main():
     for r in res:
         crc = zlib.crc32(r.bits().tobytes(), crc)
     vis = int(np.unpackbits(res[0].bits().view(np.uint8)).sum())
-    print("n=%d views=%d kernel=%d ctas=%d fma=%d changed=%d: median %.4f ms (min %.4f) -> %.2f Gobj/s, %.0f GB/s algorithmic; visible %.1f%% changed %d bits-crc %08x"
-          % (n, a.views, a.kernel, a.ctas, a.fma, a.changed, t, min(times), n / t / 1e6, bytes_alg / t / 1e6, 100.0 * vis / n, nchg, crc))
+    print("n=%d views=%d kernel=%d ctas=%d fma=%d changed=%d: median %.4f ms (min %.4f) -> %.2f Gobj/s, %.0f GB/s algorithmic; visible %.1f%% changed %d bits-crc %08x; cull kernel avg %.4f ms"
+          % (n, a.views, a.kernel, a.ctas, a.fma, a.changed, t, min(times), n / t / 1e6, bytes_alg / t / 1e6, 100.0 * vis / n, nchg, crc, k_ms / max(k_n, 1)))
 
 
 if __name__ == "__main__":
