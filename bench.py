@@ -419,19 +419,23 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = ms_total / K
     value = n_total / (ms_per_step / 1000.0)
 
-    # ---------------- e2e: same steps through the C ABI with host buffers
+    # ---------------- e2e: same steps through the C ABI with host buffers.  The result is mirrored in pinned
+    # host memory (dpcuCullResultSetHostMirror): the cull kernel's epilogue stores whole bitset lines and the
+    # compaction kernel the changed list over PCIe while they run; the step ends with dpcuCullResultSynchronize.
     n_words = (n_per + 31) // 32
     pinned_bits = [capi.HostBuffer(n_words * 4) for _ in range(views)]
     pinned_chg = [capi.HostBuffer(max(n_per, 1) * 4) for _ in range(views)]
+    pinned_cnt = [capi.HostBuffer(4) for _ in range(views)]
     hb = [p.array(np.uint32) for p in pinned_bits]
     hc = [p.array(np.uint32) for p in pinned_chg]
+    hn = [p.array(np.uint32) for p in pinned_cnt]
     pinned_vp = capi.HostBuffer(views * 64)
     hvp = pinned_vp.array(np.float32)
     import ctypes as C
     L = capi.lib()
     u32p = C.POINTER(C.c_uint32)
 
-    def e2e_step(f):
+    def e2e_step(f, mirrored=True):
         hvp[:] = cams[f].reshape(-1)           # the step's input lives in pinned host memory
         if tree is not None:
             tree.mark_dirty(1, tree.n_nodes - 1)
@@ -440,28 +444,44 @@ def run_ours(args, rank, world, local_rank):
             ctx.run(results, hvp, stream)
         d2h = 0
         for v in range(views):
-            capi.check(L.dpcuCullResultGetBits(results[v].h, hb[v].ctypes.data_as(u32p), n_words))
-            cnt = C.c_size_t()
-            capi.check(L.dpcuCullResultGetChanged(results[v].h, hc[v].ctypes.data_as(u32p), n_per, C.byref(cnt)))
-            d2h += n_words * 4 + 4 + cnt.value * 4
+            if mirrored:
+                results[v].synchronize()
+                d2h += n_words * 4 + 4 + int(hn[v][0]) * 4
+            else:
+                capi.check(L.dpcuCullResultGetBits(results[v].h, hb[v].ctypes.data_as(u32p), n_words))
+                cnt = C.c_size_t()
+                capi.check(L.dpcuCullResultGetChanged(results[v].h, hc[v].ctypes.data_as(u32p), n_per, C.byref(cnt)))
+                d2h += n_words * 4 + 4 + cnt.value * 4
         return d2h
 
-    for f in range(2):
-        e2e_step(W + K + f)
-    barrier()
-    d2h_bytes = 0
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for f in range(K):
-        d2h_bytes += e2e_step(W + K + 2 + f)
-    e1.record(stream)
-    stream.sync()
-    wall_ms = (time.perf_counter() - t0) * 1000.0
-    e2e_ms = max(e0.elapsed_ms(e1), wall_ms)
-    if dist is not None:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    def e2e_run(mirrored):
+        for f in range(2):
+            e2e_step(W + K + f, mirrored)
+        barrier()
+        nbytes = 0
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for f in range(K):
+            nbytes += e2e_step(W + K + 2 + f, mirrored)
+        e1.record(stream)
+        stream.sync()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        ms = max(e0.elapsed_ms(e1), wall_ms)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, nbytes
+
+    copy_ms, _ = e2e_run(False)                # the copy-after-the-cull getters, for comparison (reported under "also")
+    for v in range(views):
+        results[v].set_host_mirror(hb[v], hc[v], hn[v])
+    e2e_ms, d2h_bytes = e2e_run(True)
+    # the mirror really is the result: compare with the device-side getters once, untimed
+    e2e_checked = all(np.array_equal(hb[v][:n_words], results[v].bits()) and int(hn[v][0]) == results[v].changed_count()
+                      and np.array_equal(hc[v][:int(hn[v][0])], results[v].changed()) for v in range(views))
+    for v in range(views):
+        results[v].set_host_mirror(None, None, None)
     e2e_value = n_total / (e2e_ms / K / 1000.0)
     ctx.kernel_time()
     sampler.mark("load1")
@@ -502,7 +522,8 @@ def run_ours(args, rank, world, local_rank):
         roofline["step_achieved"] = (alg_upper + alg_bytes) / (ms_per_step / 1000.0) / 1e9
         roofline["step_frac"] = roofline["step_achieved"] / peak
 
-    also = {}
+    also = {"e2e_via_copy_getters": {"ms_per_step": copy_ms / K, "objects_per_s": n_total / (copy_ms / K / 1000.0),
+                                     "what": "dpcuCullRun, then dpcuCullResultGetBits / GetChanged copies (no host mirror)"}}
     # ---------------- the same step with the bitset all-gather fused into the cull kernel (N > 1)
     if world > 1 and args.gather == "also" and tree is None:
         if enable_gather():
@@ -577,8 +598,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": views * 64, "d2h_bytes_per_step": d2h_bytes // K,
                 "ms_per_step": e2e_ms / K,
+                "mirror_equals_device_result": e2e_checked,
                 "what": "camera from pinned host memory in, visibility bitset + changed list into pinned host memory out, "
-                        "through dpcuCullRun / dpcuCullResultGetBits / dpcuCullResultGetChanged"},
+                        "through dpcuCullRun / dpcuCullResultSynchronize with a host mirror (dpcuCullResultSetHostMirror): "
+                        "PCIe stores from the cull and compaction kernels, no copy after the cull"},
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
     }

@@ -181,13 +181,31 @@ int dpcuCullResultMoveBit(dpcuCullResult *result, size_t oldIndex, size_t newInd
 int dpcuCullResultDevicePointers(dpcuCullResult *result, const uint32_t **bits, size_t *nWords,
                                  const uint32_t **changedIndices, const uint32_t **changedCount);
 
+/* Result mirror in pinned host memory.  The reference's Result lives in host memory
+ * (ResultBitSet::m_results / m_changedObjects, dp/culling/ResultBitSet.h:57-61); with a mirror the
+ * cull writes the visibility words and the changed list straight into the caller's pinned,
+ * device-mapped buffers (dpcuHostBufferCreate) over PCIe while it runs - whole 128-byte lines from
+ * the cull kernel's epilogue, contiguous runs from the compaction kernel - so that after
+ * dpcuCullResultSynchronize the result is readable on the host without any further copy:
+ *   hostBits[0 .. ceil(n/32))            visibility words (nWords = capacity, checked by dpcuCullRun)
+ *   *hostChangedCount                    length of the changed list
+ *   hostChanged[0 .. min(count, cap))    ascending group indices
+ * hostBits and the hostChanged/hostChangedCount pair are optional independently; all NULL
+ * removes the mirror.  dpcuCullResultIsVisible / MoveBit keep the mirror current.  The buffers
+ * must stay valid until the mirror is changed or the result destroyed. */
+int dpcuCullResultSetHostMirror(dpcuCullResult *result, uint32_t *hostBits, size_t nWords,
+                                uint32_t *hostChanged, size_t changedCapacity, uint32_t *hostChangedCount);
+/* block the calling thread until the last cull / bit move submitted for this result is complete */
+int dpcuCullResultSynchronize(dpcuCullResult *result);
+
 /* ManagerBitSet::getBoundingBox / calculateBoundingBox, scalar branch
  * (dp/culling/src/ManagerBitSet.cpp:151-162,268-306): out6 = lower.xyz, upper.xyz */
 int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 
 /* Tuning / reporting knobs (never change results unless stated). */
 #define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
-#define DPCU_KERNEL_AUTO    0           /* 1 view: direct; >= 2 views: view-sequential packed                */
+#define DPCU_KERNEL_AUTO    0           /* 1 view: direct; >= 2 views: view-sequential packed; lines with    */
+                                        /* peer bitsets or a host mirror                                     */
 #define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */
 #define DPCU_KERNEL_STAGED  2           /* persistent CTAs, TMA bulk + cp.async staging in shared memory     */
 #define DPCU_KERNEL_VIEWS   3           /* views one after the other, packed f32x2 arithmetic                */

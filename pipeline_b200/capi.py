@@ -134,6 +134,8 @@ def _declare(L):
         "dpcuCullGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
         "dpcuCullGetKernelTime": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
         "dpcuCullResultSetPeerBits": [_vp, C.POINTER(_vp), C.c_int, C.c_size_t],
+        "dpcuCullResultSetHostMirror": [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp],
+        "dpcuCullResultSynchronize": [_vp],
         "dpcuIpcGetHandle": [_vp, C.c_char_p],
         "dpcuIpcOpen": [C.c_char_p, C.POINTER(_vp)],
         "dpcuIpcClose": [_vp],
@@ -376,10 +378,21 @@ class CullResult:
         arr = (_vp * max(len(pointers), 1))(*[(_vp(p) if p else None) for p in pointers])
         check(lib().dpcuCullResultSetPeerBits(self.h, arr, len(pointers), word_offset))
 
+    def set_host_mirror(self, bits=None, changed=None, count=None):
+        """bits / changed / count: uint32 numpy views of pinned HostBuffer memory (or None).  After
+        run() + synchronize() they hold the visibility words, the changed list and its length."""
+        self._mirror = (bits, changed, count)          # keep the views (and their buffers) alive
+        check(lib().dpcuCullResultSetHostMirror(
+            self.h, _ptr(bits), 0 if bits is None else bits.size, _ptr(changed), 0 if changed is None else changed.size, _ptr(count)))
+
+    def synchronize(self):
+        check(lib().dpcuCullResultSynchronize(self.h))
+
     def close(self):
         if self.h:
             check(lib().dpcuCullResultDestroy(self.h))
             self.h = None
+            self._mirror = None
 
     def __del__(self):
         if _shutdown:

@@ -41,7 +41,9 @@ namespace dpcu
   {
     uint32_t *bits;      // in: previous visibility, out: new visibility
     uint32_t *chg;       // out: bits that flipped
-    uint32_t *seg;       // += popc per 8192-object segment; turned into an exclusive prefix by the last CTA
+    uint32_t *seg;       // += popc per 8192-object segment; read and zeroed again by the last CTA
+    uint32_t *prefix;    // out: exclusive prefix of seg[] written by the last CTA, prefix[nSegs] = total
+    uint32_t *mirror;    // optional: the result's bitset mirror in pinned host memory (line-granular kernel)
     uint32_t *peer[kMaxPeers];   // optional: full bitsets on peer GPUs (NVLink stores)
   };
 
@@ -72,7 +74,8 @@ namespace dpcu
 #endif
 
   // The CTA that finishes last turns every view's per-segment changed counts into an exclusive
-  // prefix (seg[s] = number of changed objects before segment s, seg[nSegs] = total), in place.
+  // prefix (prefix[s] = number of changed objects before segment s, prefix[nSegs] = total) and
+  // leaves the counters and the ticket zeroed for the next cull, so no memset runs between culls.
   // Replaces the XOR + traverseBits bookkeeping of ResultBitSet::updateChanged
   // (dp/culling/src/ResultBitSet.cpp:100-107) together with the compaction kernel below.
   template <int NV>
@@ -93,7 +96,7 @@ namespace dpcu
 #pragma unroll 1
     for ( int v = 0; v < NV; ++v )
     {
-      uint32_t *seg = out[v].seg;
+      uint32_t *seg = out[v].seg, *prefix = out[v].prefix;
       uint32_t sum = 0;
       for ( uint32_t k = b; k < e; ++k ) sum += __ldcg( seg + k );
       uint32_t incl = sum;
@@ -110,12 +113,13 @@ namespace dpcu
       for ( uint32_t k = b; k < e; ++k )
       {
         const uint32_t c = __ldcg( seg + k );
-        seg[k] = run;
+        prefix[k] = run;
+        seg[k] = 0u;
         run += c;
       }
       __syncthreads();
     }
-    if ( threadIdx.x == 0 ) *done = 0u;    // ready for the next cull
+    if ( threadIdx.x == 0 ) done[0] = done[1] = 0u;    // ticket and the staged kernel's chunk counter: ready for the next cull
   }
 
   // ------------------------------------------------------------------------------------------
@@ -478,6 +482,7 @@ namespace dpcu
         if ( wordLive )
         {
           o.bits[myWord] = acc[v];
+          if ( o.mirror ) o.mirror[myWord] = acc[v];          // the same line over PCIe into pinned host memory
           for ( uint32_t p = 0; p < a.nPeers; ++p )
           {
             if ( o.peer[p] ) o.peer[p][a.peerWordOffset + myWord] = acc[v];
@@ -660,8 +665,11 @@ namespace dpcu
   struct CompactArgs
   {
     uint32_t const *chg[DPCU_MAX_VIEWS];
-    uint32_t const *seg[DPCU_MAX_VIEWS];
+    uint32_t const *prefix[DPCU_MAX_VIEWS];
     uint32_t       *changed[DPCU_MAX_VIEWS];
+    uint32_t       *hostChanged[DPCU_MAX_VIEWS];    // optional mirror of the list in pinned host memory ...
+    uint32_t       *hostCount[DPCU_MAX_VIEWS];      // ... and of its length
+    uint32_t        hostCapacity[DPCU_MAX_VIEWS];
     uint32_t        nWords;
     uint32_t        nSegs;
   };
@@ -671,9 +679,14 @@ namespace dpcu
     const uint32_t v    = blockIdx.y;
     const uint32_t s    = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t base0 = a.seg[v][s];
-    if ( a.seg[v][s + 1] == base0 ) return;          // nothing changed in this segment
+    const uint32_t base0 = a.prefix[v][s];
+    const uint32_t count = a.prefix[v][s + 1] - base0;
+    if ( s == 0 && threadIdx.x == 0 && a.hostCount[v] ) *a.hostCount[v] = a.prefix[v][a.nSegs];
+    if ( count == 0 ) return;                        // nothing changed in this segment
 
+    // the segment's indices are expanded into shared memory first, so that the list (and its host
+    // mirror, over PCIe) is written as one contiguous, coalesced run per segment
+    __shared__ uint32_t sIdx[1u << kSegObjectsLog2];
     __shared__ uint32_t sWarp[8];
     const uint32_t w = s * kSegWords + threadIdx.x;
     uint32_t c = ( w < a.nWords ) ? a.chg[v][w] : 0u;
@@ -687,15 +700,24 @@ namespace dpcu
     }
     if ( lane == 31 ) sWarp[warp] = incl;
     __syncthreads();
-    uint32_t off = base0 + incl - pc;
+    uint32_t off = incl - pc;
     for ( uint32_t k = 0; k < warp; ++k ) off += sWarp[k];
-    uint32_t *out = a.changed[v];
     const uint32_t base = w << 5;
     while ( c )
     {
       const uint32_t b = __ffs( c ) - 1;
-      out[off++] = base + b;
+      sIdx[off++] = base + b;
       c &= c - 1;
+    }
+    __syncthreads();
+    uint32_t *out = a.changed[v] + base0;
+    uint32_t *host = a.hostChanged[v];
+    const uint32_t hostRoom = a.hostCapacity[v] > base0 ? a.hostCapacity[v] - base0 : 0u;
+    for ( uint32_t k = threadIdx.x; k < count; k += 256 )
+    {
+      const uint32_t x = sIdx[k];
+      out[k] = x;
+      if ( host && k < hostRoom ) host[base0 + k] = x;
     }
   }
 
@@ -752,7 +774,7 @@ namespace dpcu
   }
 
   // ResultBitSet::onNotify (dp/culling/src/ResultBitSet.cpp:110-128)
-  __global__ void moveBitKernel( uint32_t *bits, uint32_t size, uint32_t oldIndex, uint32_t newIndex )
+  __global__ void moveBitKernel( uint32_t *bits, uint32_t size, uint32_t oldIndex, uint32_t newIndex, uint32_t *mirror )
   {
     if ( newIndex < size )
     {
@@ -761,6 +783,7 @@ namespace dpcu
       uint32_t w = bits[newIndex >> 5];
       w = value ? ( w | ( 1u << ( newIndex & 31 ) ) ) : ( w & ~( 1u << ( newIndex & 31 ) ) );
       bits[newIndex >> 5] = w;
+      if ( mirror ) mirror[newIndex >> 5] = w;
     }
   }
 
@@ -866,7 +889,7 @@ namespace dpcu
 struct dpcuCullResult
 {
   dpcuCull *ctx = nullptr;
-  dpcu::DeviceArray bits, chg, changed, counters;   // counters: done | seg[0..nSegs] (count = seg[nSegs])
+  dpcu::DeviceArray bits, chg, changed, counters;   // counters: done, chunk, -, - | seg[cap] | prefix[cap] (count = prefix[nSegs])
   size_t   n = 0;                // object count the stored bits are valid for (ResultBitSet::m_results size)
   size_t   capWords = 0;
   size_t   nSegsCap = 0;
@@ -877,10 +900,15 @@ struct dpcuCullResult
   size_t   peerWordOffset = 0;
   dpcuCullResult *next = nullptr, *prev = nullptr;
 
-  size_t   nSegs = 0;            // segments of the last run; the changed count lives at seg[nSegs]
+  // optional mirror in pinned host memory (dpcuCullResultSetHostMirror): h* = host addresses, d* = device aliases
+  uint32_t *hBits = nullptr, *dBits = nullptr, *hChanged = nullptr, *dChanged = nullptr, *hCount = nullptr, *dCount = nullptr;
+  size_t   hBitsWords = 0, hChangedCap = 0;
+
+  size_t   nSegs = 0;            // segments of the last run; the changed count lives at prefix[nSegs]
   uint32_t *donePtr() const { return static_cast<uint32_t *>( counters.ptr ); }
   uint32_t *segPtr() const { return static_cast<uint32_t *>( counters.ptr ) + 4; }
-  uint32_t *countPtr() const { return segPtr() + nSegs; }
+  uint32_t *prefixPtr() const { return segPtr() + nSegsCap; }
+  uint32_t *countPtr() const { return prefixPtr() + nSegs; }
 };
 
 struct dpcuCull
@@ -960,7 +988,7 @@ namespace dpcu
     {
       size_t cap = nSegs + 1 + nSegs / 2;
       cap = ( cap + 127 ) & ~size_t( 127 );
-      size_t entries = cap + 8;
+      size_t entries = 2 * cap + 8;
       DPCU_TRY( r->counters.reserve( entries * 4, false, stream ) );
       r->nSegsCap = cap;
       DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, r->counters.capacity, stream ) );
@@ -969,7 +997,8 @@ namespace dpcu
   }
 
   template <int NV>
-  static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf )
+  static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf,
+                         bool *mirrorsWritten )
   {
     CullArgs<NV> args;
     memset( &args, 0, sizeof args );
@@ -988,6 +1017,8 @@ namespace dpcu
       args.out[v].bits  = static_cast<uint32_t *>( r->bits.ptr );
       args.out[v].chg   = static_cast<uint32_t *>( r->chg.ptr );
       args.out[v].seg   = r->segPtr();
+      args.out[v].prefix = r->prefixPtr();
+      args.out[v].mirror = r->dBits;
       for ( int p = 0; p < kMaxPeers; ++p ) args.out[v].peer[p] = p < r->nPeers ? r->peer[p] : nullptr;
       if ( uint32_t( r->nPeers ) > args.nPeers ) args.nPeers = uint32_t( r->nPeers );
       args.peerWordOffset = uint32_t( r->peerWordOffset );
@@ -996,13 +1027,22 @@ namespace dpcu
     // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
     // issue-bound and the view-sequential packed kernel (cull_views.cuh) is the faster exact form
     const bool peers     = args.nPeers > 0;
-    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES );
+    bool mirrors = false;
+    for ( int v = 0; v < NV; ++v ) mirrors = mirrors || results[v]->dBits != nullptr;
+    // whole 128-byte lines are what NVLink peers and PCIe host mirrors want to see: both select the line-granular
+    // form.  A warp per 1024 objects needs a few million objects to fill the machine; below that the mirror is
+    // served by a copy queued behind the kernel (measured at 1 Mi objects: 86 us per step in-kernel, 79 us copied).
+    const bool mirrorLines = mirrors && !leaf && ctx->optKernel == DPCU_KERNEL_AUTO && ctx->n >= size_t( ctx->smCount ) * 32u * 1024u;
+    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || mirrorLines );
+    *mirrorsWritten = useLines && !leaf;
     if ( peers && ( ctx->optFma || leaf ) )
       return fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: peer bitsets are served by the line-granular kernel only (not the FMA or fused-leaf forms)" );
     const bool useFused  = leaf != nullptr;
     const bool useStaged = !useFused && !useLines && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
     const bool useViews  = !useFused && !useLines && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
+    // the last CTA's scan re-arms ticket and chunk counter; without a changed list nobody does
+    if ( useStaged && !ctx->optChanged ) DPCU_CUDA( cudaMemsetAsync( results[0]->donePtr(), 0, 16, stream ) );
     const size_t stagedSmem = sizeof( WarpRing ) * ( kCullThreads / 32 );
     if ( useStaged ) DPCU_CUDA( cudaFuncSetAttribute( cullStagedKernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( stagedSmem ) ) );
     args.vpFinite = 1;
@@ -1346,27 +1386,33 @@ extern "C"
         ++ctx->launches;
         r->n = n;
       }
-      // zero done | seg[0..nSegs] (one contiguous block, a few KiB)
+      // ticket and segment counters are zero here: zeroed at allocation and again by every cull's last CTA
       r->nSegs = nSegs;
-      DPCU_CUDA( cudaMemsetAsync( r->counters.ptr, 0, ( nSegs + 1 + 4 ) * 4, s ) );
       r->ran = true;
+      if ( r->hBits && r->hBitsWords < dpcu::divUp( n, 32 ) )
+        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: host mirror holds %zu bitset words, %zu needed", r->hBitsWords, dpcu::divUp( n, 32 ) );
     }
     if ( !n )
     {
-      for ( int v = 0; v < nViews; ++v ) DPCU_CUDA( results[v]->done.record( s ) );
+      for ( int v = 0; v < nViews; ++v )
+      {
+        if ( results[v]->dCount ) DPCU_CUDA( cudaMemsetAsync( results[v]->dCount, 0, 4, s ) );
+        DPCU_CUDA( results[v]->done.record( s ) );
+      }
       return DPCU_OK;
     }
     int rc = DPCU_OK;
+    bool mirrorsWritten = false;
     switch ( nViews )
     {
-      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf ); break;
-      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf ); break;
-      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf ); break;
-      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf ); break;
-      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf ); break;
-      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf ); break;
-      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf ); break;
-      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf ); break;
+      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
     }
     DPCU_TRY( rc );
     if ( ctx->optChanged )
@@ -1377,8 +1423,11 @@ extern "C"
       {
         dpcuCullResult *r = results[v];
         ca.chg[v] = static_cast<uint32_t const *>( r->chg.ptr );
-        ca.seg[v] = r->segPtr();
+        ca.prefix[v] = r->prefixPtr();
         ca.changed[v] = static_cast<uint32_t *>( r->changed.ptr );
+        ca.hostChanged[v]  = r->dChanged;
+        ca.hostCount[v]    = r->dCount;
+        ca.hostCapacity[v] = uint32_t( r->hChangedCap < 0xffffffffull ? r->hChangedCap : 0xffffffffull );
       }
       ca.nWords = uint32_t( dpcu::divUp( n, 32 ) );
       ca.nSegs = uint32_t( nSegs );
@@ -1386,6 +1435,15 @@ extern "C"
       dpcu::compactChangedKernel<<<grid, 256, 0, s>>>( ca );
       DPCU_CUDA( cudaGetLastError() );
       ++ctx->launches;
+    }
+    if ( !mirrorsWritten )
+    {
+      // kernel forms that do not store whole lines themselves (fused leaf level, explicitly chosen forms)
+      for ( int v = 0; v < nViews; ++v )
+      {
+        dpcuCullResult *r = results[v];
+        if ( r->hBits ) DPCU_CUDA( cudaMemcpyAsync( r->hBits, r->bits.ptr, dpcu::divUp( n, 32 ) * 4, cudaMemcpyDeviceToHost, s ) );
+      }
     }
     for ( int v = 0; v < nViews; ++v ) DPCU_CUDA( results[v]->done.record( s ) );
     if ( s != ctx->stream ) DPCU_CUDA( ctx->lastRun.record( s ) );
@@ -1510,6 +1568,13 @@ extern "C"
     *visible = 1;                                  // ResultBitSet::isVisible: true when index >= size
     if ( groupIndex >= r->n ) return DPCU_OK;
     dpcu::DeviceGuard guard( r->ctx->device );
+    if ( r->hBits && r->ran )
+    {
+      // the mirror holds the bits of the last cull (and of later bit moves): no device round trip per query
+      r->done.hostWait();
+      *visible = int( ( r->hBits[groupIndex >> 5] >> ( groupIndex & 31 ) ) & 1u );
+      return DPCU_OK;
+    }
     uint32_t w = 0;
     cudaStream_t s = r->ctx->stream;
     DPCU_CUDA( r->done.orderBefore( s ) );
@@ -1527,7 +1592,8 @@ extern "C"
     uint32_t o = oldIndex < ( size_t( 1 ) << 32 ) ? uint32_t( oldIndex ) : 0xffffffffu;
     cudaStream_t s = r->ctx->stream;
     DPCU_CUDA( r->done.orderBefore( s ) );
-    dpcu::moveBitKernel<<<1, 1, 0, s>>>( static_cast<uint32_t *>( r->bits.ptr ), uint32_t( r->n ), o, uint32_t( newIndex ) );
+    dpcu::moveBitKernel<<<1, 1, 0, s>>>( static_cast<uint32_t *>( r->bits.ptr ), uint32_t( r->n ), o, uint32_t( newIndex ),
+                                         r->ran ? r->dBits : nullptr );
     DPCU_CUDA( cudaGetLastError() );
     DPCU_CUDA( r->done.record( s ) );
     ++r->ctx->launches;
@@ -1554,6 +1620,44 @@ extern "C"
     for ( int p = 0; p < dpcu::kMaxPeers; ++p ) r->peer[p] = p < nPeers ? peerBits[p] : nullptr;
     r->nPeers = nPeers;
     r->peerWordOffset = wordOffset;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultSetHostMirror( dpcuCullResult *r, uint32_t *hostBits, size_t nWords, uint32_t *hostChanged, size_t changedCapacity,
+                                   uint32_t *hostChangedCount )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    DPCU_REQUIRE( !hostBits || nWords, "hostBits given with nWords == 0" );
+    DPCU_REQUIRE( !hostChanged || hostChangedCount, "hostChanged needs hostChangedCount" );
+    dpcu::DeviceGuard guard( r->ctx->device );
+    r->done.hostWait();                       // nothing in flight may still write through the old pointers
+    void *dBits = nullptr, *dChanged = nullptr, *dCount = nullptr;
+    if ( hostBits && cudaHostGetDevicePointer( &dBits, hostBits, 0 ) != cudaSuccess )
+    {
+      cudaGetLastError();
+      return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullResultSetHostMirror: hostBits is not pinned, device-mapped host memory (use dpcuHostBufferCreate)" );
+    }
+    if ( hostChanged && cudaHostGetDevicePointer( &dChanged, hostChanged, 0 ) != cudaSuccess )
+    {
+      cudaGetLastError();
+      return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullResultSetHostMirror: hostChanged is not pinned, device-mapped host memory" );
+    }
+    if ( hostChangedCount && cudaHostGetDevicePointer( &dCount, hostChangedCount, 0 ) != cudaSuccess )
+    {
+      cudaGetLastError();
+      return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullResultSetHostMirror: hostChangedCount is not pinned, device-mapped host memory" );
+    }
+    r->hBits = hostBits;       r->dBits = static_cast<uint32_t *>( dBits );       r->hBitsWords = hostBits ? nWords : 0;
+    r->hChanged = hostChanged; r->dChanged = static_cast<uint32_t *>( dChanged ); r->hChangedCap = hostChanged ? changedCapacity : 0;
+    r->hCount = hostChangedCount; r->dCount = static_cast<uint32_t *>( dCount );
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultSynchronize( dpcuCullResult *r )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    dpcu::DeviceGuard guard( r->ctx->device );
+    if ( r->done.pending ) DPCU_CUDA( cudaEventSynchronize( r->done.event ) );
     return DPCU_OK;
   }
 

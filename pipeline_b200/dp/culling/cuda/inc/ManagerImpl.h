@@ -59,7 +59,9 @@ namespace dp
         static ResultCUDASharedPtr create( GroupCUDASharedPtr const & parentGroup );
         virtual ~ResultCUDA();
 
-        /** \brief Fetch changed list + bitset of the cull that was just queued on the group's context. **/
+        /** \brief Size the pinned host mirror for the group's current object count; call before the cull is queued. **/
+        void prepare();
+        /** \brief Wait for the cull that was just queued; its bitset and changed list are in the host mirror then. **/
         void fetch();
 
         std::vector<ObjectSharedPtr> const & getChangedObjects() const { return m_changedObjects; }
@@ -78,8 +80,14 @@ namespace dp
         GroupCUDASharedPtr           m_groupParent;
         dpcuCullResult *             m_result;
         std::vector<ObjectSharedPtr> m_changedObjects;
-        std::vector<uint32_t>        m_changedIndices;
-        std::vector<uint32_t>        m_bits;          // host copy of the device bitset, m_size objects
+        // pinned host mirror of the device result (dpcuCullResultSetHostMirror): the kernels write it over PCIe
+        dpcuHostBuffer *             m_mirrorBits;
+        dpcuHostBuffer *             m_mirrorChanged;
+        dpcuHostBuffer *             m_mirrorCount;
+        uint32_t *                   m_bits;            // visibility words, m_size objects valid
+        uint32_t *                   m_changedIndices;  // ascending group indices
+        uint32_t *                   m_changedCount;
+        size_t                       m_capacity;        // objects the mirror has room for
         size_t                       m_size;
       };
 

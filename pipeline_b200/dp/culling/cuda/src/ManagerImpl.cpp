@@ -154,6 +154,13 @@ namespace dp
       ResultCUDA::ResultCUDA( GroupCUDASharedPtr const & parentGroup )
         : m_groupParent( parentGroup )
         , m_result( nullptr )
+        , m_mirrorBits( nullptr )
+        , m_mirrorChanged( nullptr )
+        , m_mirrorCount( nullptr )
+        , m_bits( nullptr )
+        , m_changedIndices( nullptr )
+        , m_changedCount( nullptr )
+        , m_capacity( 0 )
         , m_size( 0 )
       {
         DP_ASSERT( m_groupParent );
@@ -164,34 +171,64 @@ namespace dp
       ResultCUDA::~ResultCUDA()
       {
         m_groupParent->detach( this );
-        dpcuCullResultDestroy( m_result );
+        dpcuCullResultDestroy( m_result );   // waits for work in flight before the mirror goes away
+        dpcuHostBufferDestroy( m_mirrorBits );
+        dpcuHostBufferDestroy( m_mirrorChanged );
+        dpcuHostBufferDestroy( m_mirrorCount );
+      }
+
+      void ResultCUDA::prepare()
+      {
+        size_t const count = m_groupParent->getObjectCount();
+        if ( count <= m_capacity && m_mirrorBits )
+        {
+          return;
+        }
+        // grow by half so that a scene that is being populated does not re-pin memory on every cull
+        size_t capacity = count + count / 2;
+        capacity = ( ( capacity ? capacity : 1 ) + 1023 ) & ~size_t( 1023 );
+        dpcuHostBuffer * bits = nullptr, * changed = nullptr, * counter = m_mirrorCount;
+        void * bitsPtr = nullptr, * changedPtr = nullptr, * countPtr = m_changedCount;
+        DPCU_VERIFY( dpcuHostBufferCreate( &bits, capacity / 8, DPCU_HOST_MAPPED ) );
+        DPCU_VERIFY( dpcuHostBufferPointer( bits, &bitsPtr ) );
+        DPCU_VERIFY( dpcuHostBufferCreate( &changed, capacity * sizeof(uint32_t), DPCU_HOST_MAPPED ) );
+        DPCU_VERIFY( dpcuHostBufferPointer( changed, &changedPtr ) );
+        if ( !counter )
+        {
+          DPCU_VERIFY( dpcuHostBufferCreate( &counter, sizeof(uint32_t), DPCU_HOST_MAPPED ) );
+          DPCU_VERIFY( dpcuHostBufferPointer( counter, &countPtr ) );
+          *static_cast<uint32_t *>( countPtr ) = 0;
+        }
+        // the setter waits for work in flight; the old words stay readable for isVisible until the next cull
+        DPCU_VERIFY( dpcuCullResultSetHostMirror( m_result, static_cast<uint32_t *>( bitsPtr ), capacity / 32
+                                                , static_cast<uint32_t *>( changedPtr ), capacity, static_cast<uint32_t *>( countPtr ) ) );
+        if ( m_bits )
+        {
+          memcpy( bitsPtr, m_bits, ( ( m_size + 31 ) / 32 ) * sizeof(uint32_t) );
+        }
+        dpcuHostBufferDestroy( m_mirrorBits );
+        dpcuHostBufferDestroy( m_mirrorChanged );
+        m_mirrorBits = bits;       m_bits = static_cast<uint32_t *>( bitsPtr );
+        m_mirrorChanged = changed; m_changedIndices = static_cast<uint32_t *>( changedPtr );
+        m_mirrorCount = counter;   m_changedCount = static_cast<uint32_t *>( countPtr );
+        m_capacity = capacity;
       }
 
       void ResultCUDA::fetch()
       {
         dp::util::ProfileEntry p( "ResultBitSet::updateChanged" );   // same profiler key as the host diff it replaces
 
-        size_t const count = m_groupParent->getObjectCount();
-        size_t changed = 0;
-        DPCU_VERIFY( dpcuCullResultGetChangedCount( m_result, &changed ) );
-        m_changedIndices.resize( changed );
-        if ( changed )
-        {
-          DPCU_VERIFY( dpcuCullResultGetChanged( m_result, m_changedIndices.data(), changed, &changed ) );
-        }
+        // one wait, no copies: the cull kernel stored the visibility words and the compaction kernel the changed
+        // list into the pinned mirror while they ran
+        DPCU_VERIFY( dpcuCullResultSynchronize( m_result ) );
+        size_t const changed = *m_changedCount;
         m_changedObjects.clear();
         m_changedObjects.reserve( changed );
         for ( size_t i = 0; i < changed; ++i )
         {
           m_changedObjects.push_back( m_groupParent->getObject( m_changedIndices[i] ) );   // ascending group index
         }
-
-        m_size = count;
-        m_bits.resize( ( count + 31 ) / 32 );
-        if ( count )
-        {
-          DPCU_VERIFY( dpcuCullResultGetBits( m_result, m_bits.data(), m_bits.size() ) );
-        }
+        m_size = m_groupParent->getObjectCount();
       }
 
       bool ResultCUDA::isVisible( ObjectBitSetSharedPtr const & object ) const
@@ -204,20 +241,11 @@ namespace dp
 
       void ResultCUDA::onNotify( dp::util::Event const & event, dp::util::Payload * /*payload*/ )
       {
-        // ResultBitSet::onNotify, dp/culling/src/ResultBitSet.cpp:110-128 - on the device copy and on the host copy
+        // ResultBitSet::onNotify, dp/culling/src/ResultBitSet.cpp:110-128: the bit moves on the device, the same
+        // kernel stores the touched word into the host mirror; removal is not on the hot path, so wait for it
         GroupBitSet::Event const & groupEvent = static_cast<GroupBitSet::Event const &>( event );
-        size_t const newIndex = groupEvent.getNewIndex(), oldIndex = groupEvent.getOldIndex();
-        DPCU_VERIFY( dpcuCullResultMoveBit( m_result, oldIndex, newIndex ) );
-        if ( newIndex < m_size )
-        {
-          bool value = true;
-          if ( oldIndex < m_size )
-          {
-            value = !!( m_bits[oldIndex >> 5] & ( 1u << ( oldIndex & 31 ) ) );
-          }
-          if ( value ) m_bits[newIndex >> 5] |= 1u << ( newIndex & 31 );
-          else         m_bits[newIndex >> 5] &= ~( 1u << ( newIndex & 31 ) );
-        }
+        DPCU_VERIFY( dpcuCullResultMoveBit( m_result, groupEvent.getOldIndex(), groupEvent.getNewIndex() ) );
+        DPCU_VERIFY( dpcuCullResultSynchronize( m_result ) );
       }
 
       void ResultCUDA::onDestroyed( dp::util::Subject const & /*subject*/, dp::util::Payload * /*payload*/ )
@@ -319,6 +347,7 @@ namespace dp
         }
 
         groupImpl->update();
+        resultImpl->prepare();
         dpcuCullResult * handle = resultImpl->getHandle();
         DPCU_VERIFY( dpcuCullRun( groupImpl->getContext(), &handle, viewProjection.getPtr(), 1, nullptr ) );
         resultImpl->fetch();   // synchronous like the reference: the result is valid when cull returns
@@ -342,6 +371,10 @@ namespace dp
           memcpy( &matrices[16 * v], viewProjections[v].getPtr(), 16 * sizeof(float) );
         }
         groupImpl->update();
+        for ( size_t v = 0; v < results.size(); ++v )
+        {
+          std::static_pointer_cast<ResultCUDA>( results[v] )->prepare();
+        }
         DPCU_VERIFY( dpcuCullRun( groupImpl->getContext(), handles.data(), matrices.data(), static_cast<int>( results.size() ), nullptr ) );
         for ( size_t v = 0; v < results.size(); ++v )
         {

@@ -470,6 +470,8 @@ def test_run_with_tree_fused_leaf_level(capi, port, nv, binding):
     if binding == "fusion-off":
         ctx.set_option(capi.OPT_FUSE_LEAF, 0)
     res = [ctx.result_create() for _ in range(nv)]
+    mirror = _Mirror(capi, n)                        # view 0 is also mirrored in pinned host memory
+    res[0].set_host_mirror(mirror.bits, mirror.changed, mirror.count)
     view = scenes.make_look_at((0, 0, 150), (0, 0, 0), (0, 1, 0))
     vps = np.stack([scenes.mat_mul(view, scenes.make_perspective(fov, 1.3, 1.0, 500.0)) for fov in (40.0, 15.0, 75.0)][:nv])
     world = np.zeros_like(local)
@@ -501,13 +503,19 @@ def test_run_with_tree_fused_leaf_level(capi, port, nv, binding):
         assert np.array_equal(t.dirty_world()[:nw], dw), (frame, "published dirty set")
         for v in range(nv):
             want = port.cull_bits(lower4, extent4, tidx, world.reshape(-1), vps[v])
+            want_changed = port.update_changed(want, state[v], n)
             assert np.array_equal(res[v].bits(), want), (frame, v)
-            assert np.array_equal(res[v].changed(), port.update_changed(want, state[v], n)), (frame, v)
+            assert np.array_equal(res[v].changed(), want_changed), (frame, v)
+            if v == 0:
+                res[0].synchronize()
+                assert np.array_equal(mirror.bits[:len(want)], want), (frame, "host mirror bits")
+                assert int(mirror.count[0]) == len(want_changed), (frame, "host mirror count")
+                assert np.array_equal(mirror.changed[:len(want_changed)], want_changed), (frame, "host mirror list")
     # launches: 4 levels per frame unfused, 3 level kernels + the fused cull kernel (counted once) when fused
     assert t.launches() - launches_before >= 4 * 4
     for r in res:
         r.close()
-    ctx.close(), t.close()
+    ctx.close(), t.close(), mirror.close()
 
 
 @pytest.mark.parametrize("nv", [1, 3])
@@ -554,6 +562,121 @@ def test_peer_bitset_gather_in_kernel_epilogue(capi, port, nv):
         for r in res:
             r.close()
         ctx.close()
+
+
+# ------------------------------------------------------------------ result mirror in pinned host memory
+class _Mirror:
+    """pinned host buffers for one result: visibility words, changed list, its length"""
+
+    def __init__(self, capi, n, changed_capacity=None):
+        words = max((n + 31) // 32, 1)
+        cap = max(n if changed_capacity is None else changed_capacity, 1)
+        self.buffers = [capi.HostBuffer(words * 4), capi.HostBuffer(cap * 4), capi.HostBuffer(4)]
+        self.bits, self.changed, self.count = (b.array(np.uint32) for b in self.buffers)
+        self.bits[:] = 0xDEADBEEF
+        self.changed[:] = 0xDEADBEEF
+        self.count[0] = 0xDEADBEEF
+
+    def close(self):
+        for b in self.buffers:
+            b.close()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines"])
+@pytest.mark.parametrize("nv", [1, 3])
+def test_host_mirror_matches_port(capi, port, kernel, nv):
+    """dpcuCullResultSetHostMirror: after run + synchronize the pinned buffers hold exactly what
+    ResultBitSet holds on the host in the reference (bits, ascending changed list, its length),
+    for the line-granular form AUTO picks (in-kernel PCIe stores) and for every explicitly chosen
+    form (copy queued behind the kernel)."""
+    n = 1024 * 21 + 777
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C2)
+    ctx = capi.Cull(0)
+    ctx.set_option(capi.OPT_KERNEL, dict(KERNELS, auto=0)[kernel])
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    res = [ctx.result_create() for _ in range(nv)]
+    mirrors = [_Mirror(capi, n) for _ in range(nv)]
+    for r, m in zip(res, mirrors):
+        r.set_host_mirror(m.bits, m.changed, m.count)
+    state = [port.result_resize(np.zeros(0, np.uint32), 0, n) for _ in range(nv)]
+    words = (n + 31) // 32
+    for frame in range(3):
+        vps = np.ascontiguousarray(np.roll(_views_for(nv + 2), frame, axis=0)[:nv])
+        ctx.run(res, vps)
+        for v in range(nv):
+            res[v].synchronize()
+            want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vps[v])
+            want_changed = port.update_changed(want, state[v], n)
+            m = mirrors[v]
+            assert np.array_equal(m.bits[:words], want), (frame, v)
+            assert int(m.count[0]) == len(want_changed), (frame, v)
+            assert np.array_equal(m.changed[:len(want_changed)], want_changed), (frame, v)
+            # the device-side getters agree with the mirror
+            assert np.array_equal(res[v].bits(), want)
+            assert np.array_equal(res[v].changed(), want_changed)
+    # is_visible is served from the mirror; move_bit keeps it current (ResultBitSet.cpp:110-128)
+    bits0 = mirrors[0].bits[:words].copy()
+    probe = [0, 31, 32, n - 1]
+    for i in probe:
+        assert res[0].is_visible(i) == bool((bits0[i >> 5] >> (i & 31)) & 1)
+    invisible = int(np.flatnonzero(np.unpackbits(bits0.view(np.uint8), bitorder="little")[:n] == 0)[0])
+    visible = int(np.flatnonzero(np.unpackbits(bits0.view(np.uint8), bitorder="little")[:n] == 1)[0])
+    res[0].move_bit(invisible, visible)
+    res[0].synchronize()
+    assert not res[0].is_visible(visible)
+    assert not ((mirrors[0].bits[visible >> 5] >> (visible & 31)) & 1)
+    assert np.array_equal(res[0].bits(), mirrors[0].bits[:words])
+    for r in res:
+        r.close()
+    ctx.close()
+    for m in mirrors:
+        m.close()
+
+
+def test_host_mirror_capacity_and_errors(capi, port):
+    n = 50000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=7)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    r = ctx.result_create()
+    vp = _views_for(1)[0]
+    want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vp)
+    want_changed = port.update_changed(want, port.result_resize(np.zeros(0, np.uint32), 0, n), n)
+    assert len(want_changed) > 100
+    # a changed mirror smaller than the list: the count is the full length, the buffer holds its head
+    m = _Mirror(capi, n, changed_capacity=100)
+    r.set_host_mirror(m.bits, m.changed, m.count)
+    ctx.run([r], vp)
+    r.synchronize()
+    assert int(m.count[0]) == len(want_changed)
+    assert np.array_equal(m.changed[:100], want_changed[:100])
+    assert np.array_equal(r.changed(), want_changed)
+    # only the changed list mirrored / only the bits mirrored
+    r.set_host_mirror(None, m.changed, m.count)
+    ctx.run([r], _views_for(2)[1])
+    r.synchronize()
+    assert int(m.count[0]) == r.changed_count()
+    # a bits mirror that is too small is refused by the run, pageable memory by the setter
+    small = _Mirror(capi, 1000)
+    r.set_host_mirror(small.bits, None, None)
+    with pytest.raises(capi.DpcuError):
+        ctx.run([r], vp)
+    with pytest.raises(capi.DpcuError):
+        r.set_host_mirror(np.zeros(n, np.uint32), None, None)
+    # removing the mirror restores the plain path
+    r.set_host_mirror(None, None, None)
+    ctx.run([r], vp)
+    assert np.array_equal(r.bits(), want)
+    # empty group: count 0 reaches the mirror
+    ctx.set_objects(lower4[:0], extent4[:0], tidx[:0])
+    r.set_host_mirror(m.bits, m.changed, m.count)
+    m.count[0] = 77
+    ctx.run([r], vp)
+    r.synchronize()
+    assert int(m.count[0]) == 0
+    r.close(), ctx.close(), m.close(), small.close()
 
 
 # ------------------------------------------------------------------ dp/cuda layer
