@@ -235,9 +235,17 @@ class RefCull:
 class RefTree:
     """One reference ``dp::transform::Tree``."""
 
-    def __init__(self, lib):
+    def __init__(self, lib, backend=0):
+        """backend 0: dp::transform::Tree.  Drop-in test library only - 1: dp::transform::cuda::Tree edited
+        through its own type, 2: the same class edited through a base-class reference."""
         self.lib = lib
-        self.h = lib.dpref_tree_create()
+        self.backend = backend
+        if backend:
+            self.h = lib.dpref_tree_create_backend(backend)
+            if not self.h:
+                raise RuntimeError(lib.dpref_create_error().decode(errors="replace"))
+        else:
+            self.h = lib.dpref_tree_create()
 
     def close(self):
         if self.h:
@@ -275,7 +283,15 @@ class RefTree:
         self.lib.dpref_tree_update_locals(self.h, len(indices), _up(indices), _fp(locals16))
 
     def compute(self):
-        self.lib.dpref_tree_compute(self.h)
+        if self.lib.dpref_tree_compute(self.h) != 0:
+            raise RuntimeError(self.lib.dpref_create_error().decode(errors="replace"))
+
+    def device_world(self):
+        """device pointer of the world matrices (dp::transform::cuda::Tree only)"""
+        return int(self.lib.dpref_tree_device_world(self.h) or 0)
+
+    def host_mirror(self, enable):
+        self.lib.dpref_tree_host_mirror(self.h, int(bool(enable)))
 
     def count(self):
         return int(self.lib.dpref_tree_count(self.h))
@@ -333,6 +349,13 @@ def _declare_ref(lib):
     lib.dpref_tree_update_local.argtypes = [C.c_void_p, C.c_uint32, _f32p]
     lib.dpref_tree_update_locals.argtypes = [C.c_void_p, C.c_size_t, _u32p, _f32p]
     lib.dpref_tree_compute.argtypes = [C.c_void_p]
+    lib.dpref_tree_compute.restype = C.c_int
+    if hasattr(lib, "dpref_tree_create_backend"):          # the drop-in test library (tests/cpp)
+        lib.dpref_tree_create_backend.argtypes = [C.c_int]
+        lib.dpref_tree_create_backend.restype = C.c_void_p
+        lib.dpref_tree_device_world.argtypes = [C.c_void_p]
+        lib.dpref_tree_device_world.restype = C.c_void_p
+        lib.dpref_tree_host_mirror.argtypes = [C.c_void_p, C.c_int]
     lib.dpref_tree_count.argtypes = [C.c_void_p]
     lib.dpref_tree_count.restype = C.c_size_t
     lib.dpref_tree_world.argtypes = [C.c_void_p]
@@ -359,5 +382,5 @@ class Reference:
     def cull(self, backend=0) -> RefCull:
         return RefCull(self.lib, backend)
 
-    def tree(self) -> RefTree:
-        return RefTree(self.lib)
+    def tree(self, backend=0) -> RefTree:
+        return RefTree(self.lib, backend)

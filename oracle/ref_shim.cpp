@@ -22,6 +22,7 @@
 
 #ifdef DPREF_WITH_CUDA
 #include <dp/culling/cuda/Manager.h>
+#include <dp/transform/cuda/Tree.h>
 #endif
 
 #include <cstdint>
@@ -68,12 +69,42 @@ namespace
     dp::util::BitArray m_dirty;
   };
 
+  // backend 0: dp::transform::Tree (the oracle); with DPREF_WITH_CUDA backend 1: dp::transform::cuda::Tree
+  // edited through its own type (as xbar::TransformTree would hold it), backend 2: the same class edited
+  // through a base-class reference (the non-virtual addTransform / removeTransform of the reference)
   struct TreeSession
   {
-    dp::transform::Tree tree;
-    DirtyRecorder       recorder;
-    TreeSession()  { tree.attach( &recorder ); }
+    std::unique_ptr<dp::transform::Tree> owner;
+    dp::transform::Tree &                tree;
+#ifdef DPREF_WITH_CUDA
+    dp::transform::cuda::Tree *          cudaTree;
+#endif
+    bool                                 viaDerived;
+    DirtyRecorder                        recorder;
+
+    explicit TreeSession( dp::transform::Tree * t, bool derived = false )
+      : owner( t ), tree( *t )
+#ifdef DPREF_WITH_CUDA
+      , cudaTree( nullptr )
+#endif
+      , viaDerived( derived )
+    { tree.attach( &recorder ); }
     ~TreeSession() { tree.detach( &recorder ); }
+
+    dp::transform::Index add( dp::transform::Index parent, dp::math::Mat44f const & m )
+    {
+#ifdef DPREF_WITH_CUDA
+      if ( viaDerived ) return cudaTree->addTransform( parent, m );
+#endif
+      return tree.addTransform( parent, m );
+    }
+    void remove( dp::transform::Index index )
+    {
+#ifdef DPREF_WITH_CUDA
+      if ( viaDerived ) { cudaTree->removeTransform( index ); return; }
+#endif
+      tree.removeTransform( index );
+    }
   };
 
   inline dp::math::Mat44f toMat( float const * m )
@@ -336,13 +367,36 @@ extern "C"
 #endif
 
   // ---------------------------------------------------------------- dp::transform::Tree
-  void * dpref_tree_create() { return new TreeSession; }
+  void * dpref_tree_create() { return new TreeSession( new dp::transform::Tree ); }
+#ifdef DPREF_WITH_CUDA
+  void * dpref_tree_create_backend( int backend )
+  {
+    try
+    {
+      if ( backend == 0 ) return dpref_tree_create();
+      dp::transform::cuda::Tree * t = new dp::transform::cuda::Tree( 0 );
+      TreeSession * s = new TreeSession( t, backend == 1 );
+      s->cudaTree = t;
+      return s;
+    }
+    catch ( std::exception const & e ) { g_createError = e.what(); return nullptr; }
+  }
+  // device pointer of the world matrices (for dpref_cull_set_device_matrices); NULL for the host tree
+  void const * dpref_tree_device_world( void * p )
+  {
+    return TREE( p )->cudaTree ? TREE( p )->cudaTree->getDeviceWorldMatrices() : nullptr;
+  }
+  void dpref_tree_host_mirror( void * p, int enable )
+  {
+    if ( TREE( p )->cudaTree ) TREE( p )->cudaTree->setHostWorldMirror( !!enable );
+  }
+#endif
   void   dpref_tree_destroy( void * p ) { delete TREE( p ); }
 
   // returns the new index or -1 (Tree.cpp:54-77)
   int64_t dpref_tree_add( void * p, uint32_t parent, float const * local16 )
   {
-    try { return TREE( p )->tree.addTransform( parent, toMat( local16 ) ); }
+    try { return TREE( p )->add( parent, toMat( local16 ) ); }
     catch ( std::exception const & ) { return -1; }
   }
 
@@ -353,7 +407,7 @@ extern "C"
     {
       for ( size_t i = 0; i < n; ++i )
       {
-        outIndices[i] = TREE( p )->tree.addTransform( parents[i], toMat( locals16 + 16 * i ) );
+        outIndices[i] = TREE( p )->add( parents[i], toMat( locals16 + 16 * i ) );
       }
       return 0;
     }
@@ -362,7 +416,7 @@ extern "C"
 
   int dpref_tree_remove( void * p, uint32_t index )
   {
-    try { TREE( p )->tree.removeTransform( index ); return 0; }
+    try { TREE( p )->remove( index ); return 0; }
     catch ( std::exception const & ) { return 1; }
   }
 
@@ -376,9 +430,10 @@ extern "C"
     for ( size_t i = 0; i < n; ++i ) TREE( p )->tree.updateLocalMatrix( indices[i], toMat( locals16 + 16 * i ) );
   }
 
-  void dpref_tree_compute( void * p )
+  int dpref_tree_compute( void * p )
   {
-    TREE( p )->tree.compute( dp::math::cIdentity44f );
+    try { TREE( p )->tree.compute( dp::math::cIdentity44f ); return 0; }
+    catch ( std::exception const & e ) { g_createError = e.what(); return 1; }
   }
 
   size_t        dpref_tree_count( void * p ) { return TREE( p )->tree.getTransformCount(); }

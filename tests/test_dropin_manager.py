@@ -153,3 +153,125 @@ def test_multi_view_and_device_matrices_extensions(dropin, port):
         assert np.array_equal(s.visible_bits(results[v]), want), v
     s.close()
     buf.close()
+
+
+# ------------------------------------------------------------------ dp::transform::cuda::Tree
+def _drive_trees(trees, frames_check, used=None):
+    """the same edits on every tree; frames_check(frame) runs after each compute.  used[0] = 1 + the largest
+    index handed out so far (slots beyond it are uninitialised storage in the reference)."""
+    rng = np.random.RandomState(17)
+    used = used if used is not None else [0]
+
+    def locals_for(count, frame):
+        return scenes.hierarchy_locals(scenes.SEED_C3 + frame, 1, count, frame=frame)
+
+    # frame 0: build three levels (12 / 120 / 3000 nodes)
+    idx = []
+    for t in trees:
+        l0 = t.add_many(np.zeros(12, np.uint32), locals_for(12, 0))
+        l1 = t.add_many(np.repeat(l0, 10), locals_for(120, 1))
+        l2 = t.add_many(np.repeat(l1, 25), locals_for(3000, 2))
+        idx.append((l0, l1, l2))
+        t.compute()
+    for a in idx[1:]:
+        for x, y in zip(idx[0], a):
+            assert np.array_equal(x, y)                  # same index allocation
+    l0, l1, l2 = idx[0]
+    used[0] = int(l2.max()) + 1
+    frames_check(0)
+    # frame 1: scattered local edits on every level
+    pick = np.unique(np.concatenate([rng.choice(l0, 3), rng.choice(l1, 9), rng.choice(l2, 200)])).astype(np.uint32)
+    new = scenes.hierarchy_locals(scenes.SEED_C3 + 5, 1, len(pick), frame=4)
+    for t in trees:
+        t.update_locals(pick, new)
+        t.compute()
+    frames_check(1)
+    # frame 2: nothing dirty
+    for t in trees:
+        t.compute()
+    frames_check(2)
+    # frame 3: topology edits between computes - remove leaves (orphaning nothing), add new subtrees
+    gone = rng.choice(l2, 40, replace=False).astype(np.uint32)
+    for t in trees:
+        for g in gone:
+            t.remove(int(g))
+        fresh = t.add_many(np.resize(l1, 60), locals_for(60, 6))
+        deeper = t.add_many(np.repeat(fresh[:10], 4), locals_for(40, 7))        # a fourth level
+        t.update_locals(l0[:2], locals_for(2, 8))
+        t.compute()
+        used[0] = max(used[0], int(fresh.max()) + 1, int(deeper.max()) + 1)
+    frames_check(3)
+    # frame 4: a contiguous run of locals (whole level) rewritten
+    for t in trees:
+        t.update_locals(l1, locals_for(len(l1), 9))
+        t.compute()
+    frames_check(4)
+    # frame 5: remove + add that leaves every level size unchanged (the case only the explicit
+    # topology flag catches when edits go through the derived type)
+    victim = int(l2[7])
+    for t in trees:
+        t.remove(victim)
+        again = t.add_many(np.asarray([l1[3]], np.uint32), locals_for(1, 10))
+        t.compute()
+    frames_check(5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("backend", [1, 2])
+def test_transform_tree_dropin_same_driver(dropin, backend):
+    """dp::transform::Tree and dp::transform::cuda::Tree behind the same calls: world matrices, the
+    published dirty set (EventWorldMatricesChanged) and index allocation must be identical frame by
+    frame - for edits through the derived type (backend 1) and through a base reference (backend 2;
+    the final same-size remove + add is skipped there, see Tree.h)."""
+    ref, dev = dropin.tree(0), dropin.tree(backend)
+    used = [0]
+
+    def check(frame):
+        if backend == 2 and frame == 5:
+            return
+        assert ref.count() == dev.count()
+        assert np.array_equal(ref.dirty_world(), dev.dirty_world()), (frame, "published dirty set")
+        assert np.array_equal(ref.world()[:used[0]].view(np.uint32), dev.world()[:used[0]].view(np.uint32)), (frame, "world matrices")
+
+    _drive_trees([ref, dev], check, used)
+    ref.close(), dev.close()
+
+
+@pytest.mark.gpu
+def test_transform_tree_feeds_cuda_manager_zero_copy(dropin):
+    """SURVEY.md 8f rank 1 + 3: the reference frame loop (TransformTree::compute, then CullingImpl::cull with
+    the tree's world matrices) on both stacks - cpu: Tree -> groupSetMatrices(host world) -> cpu::Manager;
+    cuda: cuda::Tree -> groupSetDeviceMatrices(device world) -> cuda::Manager, no matrix ever re-uploaded,
+    host world mirror off.  Bitsets and changed lists must match every frame."""
+    ref_tree, dev_tree = dropin.tree(0), dropin.tree(1)
+    dev_tree.host_mirror(False)
+    cpu, gpu = dropin.cull(0), dropin.cull(1)
+    rc, rg = cpu.result_create(), gpu.result_create()
+    state = {"leaves": None}
+    view = scenes.make_look_at((0, 0, 30), (0, 0, 0), (0, 1, 0))      # inside the cloud of nodes: some are behind the eye
+    vps = [scenes.mat_mul(view, scenes.make_perspective(fov, 1.3, 1.0, 600.0)) for fov in (35.0, 15.0, 50.0, 35.0, 25.0, 45.0)]
+
+    def check(frame):
+        n_nodes = ref_tree.count()
+        if frame == 0:
+            # one object per node of the deepest level that exists after the first frame
+            rng = np.random.RandomState(2)
+            n = 3000
+            lower4, extent4, upper4, _, _ = cases.random_case(n)
+            tidx = rng.randint(1, 1 + 12 + 120 + 3000, size=n).astype(np.uint32)
+            for s in (cpu, gpu):
+                s.add_objects(np.ascontiguousarray(lower4[:, :3] * 0.3), np.ascontiguousarray(upper4[:, :3] * 0.3), tidx)
+        cpu.set_matrices(ref_tree.world_view(), 64, n_nodes)
+        for i in np.flatnonzero(np.unpackbits(ref_tree.dirty_world().view(np.uint8), bitorder="little")):
+            cpu.matrix_changed(int(i))                                   # what the dormant TransformObserver would do
+        gpu.set_device_matrices(dev_tree.device_world(), n_nodes)
+        cpu.cull(rc, vps[frame])
+        gpu.cull(rg, vps[frame])
+        assert np.array_equal(cpu.visible_bits(rc), gpu.visible_bits(rg)), frame
+        assert np.array_equal(cpu.changed(rc), gpu.changed(rg)), frame
+        if frame == 0:
+            vis = int(np.unpackbits(cpu.visible_bits(rc).view(np.uint8)).sum())
+            assert 0 < vis < 3000
+
+    _drive_trees([ref_tree, dev_tree], check)
+    cpu.close(), gpu.close(), ref_tree.close(), dev_tree.close()
