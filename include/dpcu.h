@@ -181,6 +181,16 @@ int dpcuCullResultMoveBit(dpcuCullResult *result, size_t oldIndex, size_t newInd
 int dpcuCullResultDevicePointers(dpcuCullResult *result, const uint32_t **bits, size_t *nWords,
                                  const uint32_t **changedIndices, const uint32_t **changedCount);
 
+/* GPU-side consumer of the result (replaces the host loop over changed objects in
+ * DrawableManagerDefault::cull, dp/sg/renderer/rix/gl/src/DrawableManagerDefault.cpp:351-378, for renderers
+ * that draw from the GPU): build, on the device, the ASCENDING list of group indices that are visible
+ * after the last cull.  *count (one u32 in device memory) can be bound as the instance count of an
+ * indirect draw, indices as the instance -> object table.  Valid until the next cull on this result;
+ * moved bits (dpcuCullResultMoveBit) are reflected by building again. */
+int dpcuCullResultBuildVisibleList(dpcuCullResult *result, dpcuStream *stream);
+int dpcuCullResultVisibleDevicePointers(dpcuCullResult *result, const uint32_t **indices, const uint32_t **count);
+int dpcuCullResultGetVisible(dpcuCullResult *result, uint32_t *hostIndices, size_t capacity, size_t *count);
+
 /* Result mirror in pinned host memory.  The reference's Result lives in host memory
  * (ResultBitSet::m_results / m_changedObjects, dp/culling/ResultBitSet.h:57-61); with a mirror the
  * cull writes the visibility words and the changed list straight into the caller's pinned,

@@ -134,6 +134,9 @@ def _declare(L):
         "dpcuCullGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
         "dpcuCullGetKernelTime": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
         "dpcuCullResultSetPeerBits": [_vp, C.POINTER(_vp), C.c_int, C.c_size_t],
+        "dpcuCullResultBuildVisibleList": [_vp, _vp],
+        "dpcuCullResultVisibleDevicePointers": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
+        "dpcuCullResultGetVisible": [_vp, _u32p, C.c_size_t, _szp],
         "dpcuCullResultSetHostMirror": [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp],
         "dpcuCullResultSynchronize": [_vp],
         "dpcuIpcGetHandle": [_vp, C.c_char_p],
@@ -377,6 +380,21 @@ class CullResult:
     def set_peer_bits(self, pointers, word_offset):
         arr = (_vp * max(len(pointers), 1))(*[(_vp(p) if p else None) for p in pointers])
         check(lib().dpcuCullResultSetPeerBits(self.h, arr, len(pointers), word_offset))
+
+    def build_visible_list(self, stream=None):
+        check(lib().dpcuCullResultBuildVisibleList(self.h, stream.h if stream else None))
+
+    def visible_device_pointers(self):
+        idx, cnt = _vp(), _vp()
+        check(lib().dpcuCullResultVisibleDevicePointers(self.h, C.byref(idx), C.byref(cnt)))
+        return idx.value or 0, cnt.value or 0
+
+    def visible(self):
+        c = C.c_size_t()
+        check(lib().dpcuCullResultGetVisible(self.h, None, 0, C.byref(c)))
+        out = np.empty(max(c.value, 1), dtype=np.uint32)
+        check(lib().dpcuCullResultGetVisible(self.h, out.ctypes.data_as(_u32p), c.value, C.byref(c)))
+        return out[:c.value].copy()
 
     def set_host_mirror(self, bits=None, changed=None, count=None):
         """bits / changed / count: uint32 numpy views of pinned HostBuffer memory (or None).  After

@@ -722,6 +722,37 @@ namespace dpcu
   }
 
   // ------------------------------------------------------------------------------------------
+  // Visible-instance list (the consumer of the result stays on the GPU).
+  // Per-segment popcounts of the visibility words, scanned by the last CTA exactly like the
+  // changed counts; compactChangedKernel then expands bits[] instead of chg[].
+  __global__ void __launch_bounds__( kCullThreads ) segmentPopcountKernel( uint32_t const *bits, uint32_t nWords, uint32_t nSegs,
+                                                                          uint32_t *seg, uint32_t *prefix, uint32_t *done )
+  {
+    __shared__ uint32_t sPart[kCullThreads / 32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for ( uint32_t s = blockIdx.x; s < nSegs; s += gridDim.x )
+    {
+      const uint32_t w = s * kSegWords + threadIdx.x;
+      uint32_t pc = ( w < nWords ) ? __popc( bits[w] ) : 0u;
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 ) pc += __shfl_xor_sync( 0xffffffffu, pc, d );
+      if ( lane == 0 ) sPart[warp] = pc;
+      __syncthreads();
+      if ( threadIdx.x == 0 )
+      {
+        uint32_t total = 0;
+        for ( int k = 0; k < kCullThreads / 32; ++k ) total += sPart[k];
+        seg[s] = total;
+      }
+      __syncthreads();
+    }
+    ViewOut out[1];
+    out[0].seg = seg;
+    out[0].prefix = prefix;
+    scanSegmentsInLastCta<1>( out, nSegs, done );
+  }
+
+  // ------------------------------------------------------------------------------------------
   // object upload: pack transformIndex into lower.w, zero extent.w, track the largest index
   __global__ void packObjectsKernel( float4 const *lower, float4 const *extent, uint32_t const *tidx, uint32_t n,
                                      float4 *lowerIdx, float4 *extentOut, uint32_t *maxIndex )
@@ -900,6 +931,9 @@ struct dpcuCullResult
   size_t   peerWordOffset = 0;
   dpcuCullResult *next = nullptr, *prev = nullptr;
 
+  dpcu::DeviceArray visible, visCounters;           // dpcuCullResultBuildVisibleList: indices | done[4], seg[cap], prefix[cap]
+  size_t   visSegsCap = 0, visSegs = 0;
+  bool     visBuilt = false;
   // optional mirror in pinned host memory (dpcuCullResultSetHostMirror): h* = host addresses, d* = device aliases
   uint32_t *hBits = nullptr, *dBits = nullptr, *hChanged = nullptr, *dChanged = nullptr, *hCount = nullptr, *dCount = nullptr;
   size_t   hBitsWords = 0, hChangedCap = 0;
@@ -1340,6 +1374,7 @@ extern "C"
     r->done.hostWait();
     r->done.destroy();
     r->bits.release(); r->chg.release(); r->changed.release(); r->counters.release();
+    r->visible.release(); r->visCounters.release();
     if ( r->prev ) r->prev->next = r->next; else ctx->results = r->next;
     if ( r->next ) r->next->prev = r->prev;
     delete r;
@@ -1389,6 +1424,7 @@ extern "C"
       // ticket and segment counters are zero here: zeroed at allocation and again by every cull's last CTA
       r->nSegs = nSegs;
       r->ran = true;
+      r->visBuilt = false;
       if ( r->hBits && r->hBitsWords < dpcu::divUp( n, 32 ) )
         return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: host mirror holds %zu bitset words, %zu needed", r->hBitsWords, dpcu::divUp( n, 32 ) );
     }
@@ -1620,6 +1656,83 @@ extern "C"
     for ( int p = 0; p < dpcu::kMaxPeers; ++p ) r->peer[p] = p < nPeers ? peerBits[p] : nullptr;
     r->nPeers = nPeers;
     r->peerWordOffset = wordOffset;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultBuildVisibleList( dpcuCullResult *r, dpcuStream *stream )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    dpcuCull *ctx = r->ctx;
+    dpcu::DeviceGuard guard( ctx->device );
+    cudaStream_t s = stream ? stream->stream : ctx->stream;
+    const size_t n = r->n;
+    const size_t nSegs = dpcu::divUp( n, size_t( 1 ) << dpcu::kSegObjectsLog2 );
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    if ( nSegs + 1 > r->visSegsCap )
+    {
+      size_t cap = ( nSegs + 1 + nSegs / 2 + 127 ) & ~size_t( 127 );
+      DPCU_TRY( r->visCounters.reserve( ( 2 * cap + 8 ) * 4, false, s ) );
+      DPCU_CUDA( cudaMemsetAsync( r->visCounters.ptr, 0, r->visCounters.capacity, s ) );
+      r->visSegsCap = cap;
+    }
+    DPCU_TRY( r->visible.reserve( ( n ? n : 1 ) * 4, false, s ) );
+    uint32_t *done = static_cast<uint32_t *>( r->visCounters.ptr ), *seg = done + 4, *prefix = seg + r->visSegsCap;
+    r->visSegs = nSegs;
+    if ( !n )
+    {
+      DPCU_CUDA( cudaMemsetAsync( prefix, 0, 4, s ) );
+    }
+    else
+    {
+      int grid = int( nSegs < size_t( ctx->smCount ) * 8 ? nSegs : size_t( ctx->smCount ) * 8 );
+      dpcu::segmentPopcountKernel<<<grid, dpcu::kCullThreads, 0, s>>>( static_cast<uint32_t const *>( r->bits.ptr ), uint32_t( dpcu::divUp( n, 32 ) ),
+                                                                       uint32_t( nSegs ), seg, prefix, done );
+      DPCU_CUDA( cudaGetLastError() );
+      dpcu::CompactArgs ca;
+      memset( &ca, 0, sizeof ca );
+      ca.chg[0]     = static_cast<uint32_t const *>( r->bits.ptr );
+      ca.prefix[0]  = prefix;
+      ca.changed[0] = static_cast<uint32_t *>( r->visible.ptr );
+      ca.nWords = uint32_t( dpcu::divUp( n, 32 ) );
+      ca.nSegs  = uint32_t( nSegs );
+      dpcu::compactChangedKernel<<<dim3( ca.nSegs, 1 ), 256, 0, s>>>( ca );
+      DPCU_CUDA( cudaGetLastError() );
+      ctx->launches += 2;
+    }
+    DPCU_CUDA( r->done.record( s ) );
+    r->visBuilt = true;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultVisibleDevicePointers( dpcuCullResult *r, const uint32_t **indices, const uint32_t **count )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    if ( !r->visBuilt ) return dpcu::fail( DPCU_ERR_NOT_READY, "dpcuCullResultVisibleDevicePointers: no visible list built since the last cull" );
+    if ( indices ) *indices = static_cast<uint32_t const *>( r->visible.ptr );
+    if ( count ) *count = static_cast<uint32_t const *>( r->visCounters.ptr ) + 4 + r->visSegsCap + r->visSegs;
+    return DPCU_OK;
+  }
+
+  int dpcuCullResultGetVisible( dpcuCullResult *r, uint32_t *hostIndices, size_t capacity, size_t *count )
+  {
+    DPCU_REQUIRE( r && count, "NULL argument" );
+    *count = 0;
+    const uint32_t *dIdx = nullptr, *dCount = nullptr;
+    DPCU_TRY( dpcuCullResultVisibleDevicePointers( r, &dIdx, &dCount ) );
+    dpcu::DeviceGuard guard( r->ctx->device );
+    cudaStream_t s = r->ctx->stream;
+    uint32_t c = 0;
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    DPCU_CUDA( cudaMemcpyAsync( &c, dCount, 4, cudaMemcpyDeviceToHost, s ) );
+    DPCU_CUDA( cudaStreamSynchronize( s ) );
+    *count = c;
+    size_t take = c < capacity ? c : capacity;
+    if ( take )
+    {
+      DPCU_REQUIRE( hostIndices, "hostIndices is NULL" );
+      DPCU_CUDA( cudaMemcpyAsync( hostIndices, dIdx, take * 4, cudaMemcpyDeviceToHost, s ) );
+      DPCU_CUDA( cudaStreamSynchronize( s ) );
+    }
     return DPCU_OK;
   }
 

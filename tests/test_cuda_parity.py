@@ -679,6 +679,39 @@ def test_host_mirror_capacity_and_errors(capi, port):
     r.close(), ctx.close(), m.close(), small.close()
 
 
+# ------------------------------------------------------------------ visible-instance list built on the device
+@pytest.mark.parametrize("n", [0, 1, 33, 8191, 8192, 8193, 100003])
+def test_visible_list_is_the_ascending_set_bits(capi, port, n):
+    """dpcuCullResultBuildVisibleList: the GPU-built list equals the ascending indices
+    of the set bits of the oracle's visibility words; it follows bit moves and is invalidated by a new cull."""
+    lower4, extent4, upper4, mats, tidx = cases.random_case(max(n, 1))
+    lower4, extent4, tidx = lower4[:n], extent4[:n], tidx[:n]
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    r = ctx.result_create()
+    with pytest.raises(capi.DpcuError):
+        r.visible_device_pointers()                      # nothing built yet
+    for vp in cases.frames(2):
+        ctx.run([r], vp)
+        with pytest.raises(capi.DpcuError):
+            r.visible_device_pointers()                  # a new cull invalidates the previous list
+        r.build_visible_list()
+        want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vp) if n else np.zeros(0, np.uint32)
+        want_list = np.flatnonzero(np.unpackbits(want.view(np.uint8), bitorder="little")[:n]).astype(np.uint32)
+        assert np.array_equal(r.visible(), want_list)
+        idx_ptr, cnt_ptr = r.visible_device_pointers()
+        assert idx_ptr and cnt_ptr
+    if n > 40:
+        vis = r.visible()
+        hidden = np.setdiff1d(np.arange(n, dtype=np.uint32), vis)
+        if len(vis) and len(hidden):
+            r.move_bit(int(hidden[0]), int(vis[0]))     # vis[0] becomes invisible (ResultBitSet.cpp:110-128)
+            r.build_visible_list()
+            assert np.array_equal(r.visible(), vis[1:])
+    r.close(), ctx.close()
+
+
 # ------------------------------------------------------------------ dp/cuda layer
 def test_buffers_streams_events(capi):
     s = capi.Stream()

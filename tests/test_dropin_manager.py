@@ -39,6 +39,11 @@ def test_dropin_library_fails_loudly_without_gpu(dropin):
     with pytest.raises(RuntimeError) as e:
         dropin.cull(1)             # dp::culling::cuda::Manager::create() throws: no silent CPU path
     assert "no CPU fallback" in str(e.value)
+    host_tree = dropin.tree(0)     # likewise dp::transform::Tree vs dp::transform::cuda::Tree
+    host_tree.close()
+    with pytest.raises(RuntimeError) as e:
+        dropin.tree(1)
+    assert "no CPU fallback" in str(e.value)
 
 
 @pytest.mark.gpu

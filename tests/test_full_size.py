@@ -103,6 +103,9 @@ def test_c4_sixty_four_million_single_view(capi, port, n):
     sc.ctx.run([r], scenes.orbit_camera(5))
     assert r.changed_count() == 0
     assert np.array_equal(r.bits(), old)
+    # the device-built visible-instance list is the ascending set bits
+    r.build_visible_list()
+    assert np.array_equal(r.visible(), _set_bits(old, n))
     # every kernel form yields the same words at full size
     crc = zlib.crc32(old.tobytes())
     for kernel in (capi.KERNEL_DIRECT, capi.KERNEL_VIEWS, capi.KERNEL_LINES, capi.KERNEL_STAGED):
