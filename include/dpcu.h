@@ -221,6 +221,8 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 #define DPCU_KERNEL_VIEWS   3           /* views one after the other, packed f32x2 arithmetic                */
 #define DPCU_KERNEL_LINES   4           /* a warp per 1024 objects, whole 128-byte bitset lines; always used */
                                         /* when peer bitsets are set (dpcuCullResultSetPeerBits)             */
+#define DPCU_KERNEL_VIEWS_CHAINS 5      /* the views form with three predicate chains per axis instead of a  */
+                                        /* counted compare (the earlier formulation; kept for comparison)    */
 #define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */

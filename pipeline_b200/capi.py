@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF = 1, 2, 3, 4, 5, 6
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS = 0, 1, 2, 3, 4, 5
 MAX_VIEWS = 8
 
 _vp = C.c_void_p

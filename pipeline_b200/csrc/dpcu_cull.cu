@@ -196,17 +196,53 @@ namespace dpcu
   // OBB is built once, then the views run one after the other through packed f32x2 arithmetic.
   // Lane v of each warp owns view v's epilogue (previous word, new word, flipped bits, segment
   // counter, peer stores), so the V epilogues of a warp are one divergent block instead of V.
-  template <int NV>
-  __global__ void __launch_bounds__( kCullThreads, 2 )
+#ifndef DPCU_VIEWS_MIN_CTAS
+#define DPCU_VIEWS_MIN_CTAS 4
+#endif
+#ifndef DPCU_VIEWS_PREFETCH
+#define DPCU_VIEWS_PREFETCH 1
+#endif
+  __device__ __forceinline__ void prefetchL2( void const *p )
+  {
+    asm volatile( "prefetch.global.L2 [%0];" :: "l"( p ) );
+  }
+
+  template <int NV, bool kCount>
+  __global__ void __launch_bounds__( kCullThreads, DPCU_VIEWS_MIN_CTAS )
   cullViewsKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane = threadIdx.x & 31u;
+#if DPCU_VIEWS_PREFETCH
+    // Two dependent DRAM round trips (object -> its matrix) head every tile and this kernel runs at
+    // 8 warps per scheduler at most, so a third of the warp time was spent waiting on them (ncu:
+    // long_scoreboard 2.05 warps per issue).  The transform index of this thread's object two tiles
+    // ahead is fetched now (one register; it also pulls that tile's lowerIdx lines in), the index
+    // fetched a tile ago turns into an L2 prefetch of the next tile's matrix and extent lines.
+    const uint32_t strideObjects = gridDim.x * kCullThreads;
+    uint32_t idxNext = 0;
+    {
+      const uint32_t i1 = blockIdx.x * kCullThreads + threadIdx.x + strideObjects;
+      if ( i1 < a.n && i1 >= strideObjects ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
+    }
+#endif
     for ( uint32_t tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x )
     {
       const uint32_t i        = tile * kCullThreads + threadIdx.x;
       const bool     live     = i < a.n;
       const bool     wordLive = ( i - lane ) < a.n;
       const uint32_t word     = i >> 5;
+#if DPCU_VIEWS_PREFETCH
+      uint32_t idxNext2 = 0;
+      {
+        const uint32_t i1 = i + strideObjects, i2 = i1 + strideObjects;
+        if ( i2 < a.n && i2 > i1 ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i2 ) + 3 );
+        if ( i1 < a.n && i1 > i )
+        {
+          prefetchL2( a.mats + 4ull * idxNext );
+          if ( ( lane & 7u ) == 0 ) prefetchL2( a.extent + i1 );
+        }
+      }
+#endif
 
       uint32_t oldBits = 0;
       if ( lane < NV && wordLive ) oldBits = a.out[lane].bits[word];
@@ -228,7 +264,7 @@ namespace dpcu
       const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
       const ObbPairs ob = broadcastObb( obb );
 
-      const uint32_t myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+      const uint32_t myWord = fast ? cullViews<NV, true, kCount>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false, kCount>( ob, a.vp, a.onePair, live, lane );
 
       if ( lane < NV && wordLive )
       {
@@ -241,6 +277,9 @@ namespace dpcu
           if ( c ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
         }
       }
+#if DPCU_VIEWS_PREFETCH
+      idxNext = idxNext2;
+#endif
     }
     if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
@@ -418,8 +457,9 @@ namespace dpcu
   // over NVLink: whole lines on the wire, no barrier, no shared memory, no separate collective.
   // (Per-word 4-byte peer stores from the direct kernel were measured at 1.87 ms per 64 Mi-object
   // step on 8 GPUs; a shared-memory hand-over with two CTA barriers at 1.21 ms; the cull alone 0.98 ms.)
+  // measured at 64 Mi objects: 2 views 1.55 / 1.23 / 1.16 ms and 6 views 2.82 / 2.61 / 2.64 ms at 2 / 3 / 4 CTAs per SM
   template <int NV>
-  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : 2 )
+  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : ( NV <= 3 ? 4 : 3 ) )
   cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane   = threadIdx.x & 31u;
@@ -1073,7 +1113,8 @@ namespace dpcu
       return fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: peer bitsets are served by the line-granular kernel only (not the FMA or fused-leaf forms)" );
     const bool useFused  = leaf != nullptr;
     const bool useStaged = !useFused && !useLines && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
-    const bool useViews  = !useFused && !useLines && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
+    const bool useChains = ctx->optKernel == DPCU_KERNEL_VIEWS_CHAINS;
+    const bool useViews  = !useFused && !useLines && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || useChains || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
     // the last CTA's scan re-arms ticket and chunk counter; without a changed list nobody does
     if ( useStaged && !ctx->optChanged ) DPCU_CUDA( cudaMemsetAsync( results[0]->donePtr(), 0, 16, stream ) );
@@ -1094,7 +1135,8 @@ namespace dpcu
       else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV>, kCullThreads, 0 );
       else if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
       else if ( useStaged ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullStagedKernel<NV>, kCullThreads, stagedSmem );
-      else if ( useViews ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV>, kCullThreads, 0 );
+      else if ( useViews && useChains ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV, false>, kCullThreads, 0 );
+      else if ( useViews ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV, true>, kCullThreads, 0 );
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullDirectKernel<NV>, kCullThreads, 0 );
       if ( perSm <= 0 ) perSm = 1;
     }
@@ -1145,7 +1187,8 @@ namespace dpcu
     }
     else if ( useViews )
     {
-      cullViewsKernel<NV><<<grid, kCullThreads, 0, stream>>>( args );
+      if ( useChains ) cullViewsKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
+      else             cullViewsKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
     }
     else
@@ -1827,7 +1870,7 @@ extern "C"
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     switch ( option )
     {
-      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 4, "kernel must be 0..4" ); ctx->optKernel = value; break;
+      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 5, "kernel must be 0..5" ); ctx->optKernel = value; break;
       case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;

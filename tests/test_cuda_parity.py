@@ -202,7 +202,7 @@ def test_multi_view_equals_single_views(capi, port):
 
 
 # ------------------------------------------------------------------ both exact kernel forms, 1..8 views
-KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4}
+KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5}
 
 
 def _views_for(nv, extra=()):

@@ -46,17 +46,29 @@ def test_exact_kernels_have_no_contracted_multiply_add(sass):
     for name, body in exact.items():
         scalar = [i for i in body if re.match(r"(@!?U?P\d+\s+)?FFMA\b", i)]
         assert not scalar, "%s contains scalar FFMA: %s" % (name, scalar[:3])
-        packed = [i for i in body if re.match(r"(@!?U?P\d+\s+)?FFMA2\b", i)]
-        # every FFMA2 must be addProd: (packed product) * one + (packed product); `one` lives in
-        # ONE uniform register pair per kernel, and the multiplicand is never a scalar broadcast
-        multipliers = set()
-        for i in packed:
+        # every FFMA2 must be addProd: (packed product) * one + (packed product).  `one` arrives as a kernel
+        # argument: the uniform register used as multiplier must have been loaded, by the nearest preceding
+        # definition in program order, from ONE fixed constant-bank address per kernel (CullArgs::onePair),
+        # never from the indexed view-projection rows, and the multiplicand is never a scalar broadcast
+        sources = set()
+        for pos, i in enumerate(body):
+            if not re.match(r"(@!?U?P\d+\s+)?FFMA2\b", i):
+                continue
             ops = [o.strip() for o in i.split(None, 1)[1].rstrip(" ;").split(",")]
             assert len(ops) == 4, i
             assert ops[1].endswith(".F32x2.HI_LO") and ops[1].startswith("R"), "%s: %s" % (name, i)
             assert ops[2].startswith("UR"), "%s: %s" % (name, i)
-            multipliers.add(ops[2])
-        assert len(multipliers) <= 1, "%s: FFMA2 with different multipliers %s" % (name, multipliers)
+            ur = ops[2].split(".")[0]
+            for back in range(pos - 1, -1, -1):
+                m = re.match(r"(@!?U?P\d+\s+)?(LDCU(?:\.\d+)?|UMOV)\s+%s,\s*(\S+)\s*;" % ur, body[back])
+                if m:
+                    if m.group(2) != "UMOV":            # (a UMOV copies a half loaded elsewhere)
+                        sources.add(m.group(3))
+                    break
+            else:
+                raise AssertionError("%s: no definition of %s before %s" % (name, ur, i))
+        assert len(sources) <= 1, "%s: FFMA2 multipliers come from %s" % (name, sources)
+        assert all("UR" not in a for a in sources), "%s: FFMA2 multiplier loaded from an indexed address %s" % (name, sources)
 
 
 def test_fma_variant_is_really_fused(sass):
