@@ -286,6 +286,11 @@ int dpcuTreeLocalDevicePointer(dpcuTree *tree, float **deviceMatrices, size_t *n
 int dpcuTreeGetWorld(dpcuTree *tree, size_t first, size_t count, float *hostMatrices);
 int dpcuTreeGetDirtyWorld(dpcuTree *tree, uint32_t *hostWords, size_t nWords);
 int dpcuTreeGetLaunchCount(const dpcuTree *tree, uint64_t *launches);
+/* Tuning knob (never changes results): levels with at least this many nodes are propagated by the
+ * persistent one-thread-per-node kernel with coalesced matrix traffic, smaller ones by the
+ * four-threads-per-node kernel.  Default 65536; 0 = always the wide form, SIZE_MAX = never. */
+#define DPCU_TREE_OPT_WIDE_MIN_NODES 1
+int dpcuTreeSetOption(dpcuTree *tree, int option, size_t value);
 
 /* One frame of the reference's update + cull (SceneTree::update -> Tree::compute, then
  * CullingImpl::cull: dp/sg/xbar/src/SceneTree.cpp:153-170, dp/sg/xbar/culling/src/CullingImpl.cpp:126-144)

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF = 1, 2, 3, 4, 5, 6
+TREE_OPT_WIDE_MIN_NODES = 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS = 0, 1, 2, 3, 4, 5
 MAX_VIEWS = 8
 
@@ -154,6 +155,7 @@ def _declare(L):
         "dpcuTreeGetWorld": [_vp, C.c_size_t, C.c_size_t, _vp],
         "dpcuTreeGetDirtyWorld": [_vp, _u32p, C.c_size_t],
         "dpcuTreeGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
+        "dpcuTreeSetOption": [_vp, C.c_int, C.c_size_t],
         "dpcuSceneGenerate": [C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32, _vp, _vp, _vp, _vp],
     }
     for name, args in sig.items():
@@ -578,6 +580,9 @@ class Tree:
         words = np.zeros((self.n_nodes + 31) // 32, dtype=np.uint32)
         check(lib().dpcuTreeGetDirtyWorld(self.h, words.ctypes.data_as(_u32p), len(words)))
         return words
+
+    def set_option(self, option, value):
+        check(lib().dpcuTreeSetOption(self.h, option, value))
 
     def launches(self):
         v = C.c_uint64()

@@ -5,12 +5,18 @@
 //              entries[E]                         uint2 {parent, transform}, levels back to back
 //              dirtyLocal / dirtyWorld            u32 bit words over node indices
 //
-// K1 runs one launch per level.  Four threads cooperate on a node: thread r computes row r of
-// world[t] = local[t] * world[parent] with the reference's association order (a2), so local
-// reads and world writes are 16-byte accesses contiguous across the warp when a level's nodes
-// are contiguous, and the four parent rows are one 64-byte broadcast per node that siblings
-// share through L1/L2.  Compiled with -fmad=false.
+// K1 runs one launch per level, in one of two forms:
+//   treeLevelKernel      four threads per node, thread r computes row r of world[t] = local[t] *
+//                        world[parent] with the reference's association order (a2); one short
+//                        dependent chain per thread - used for small levels (latency bound anyway);
+//   treeLevelWideKernel  one thread per node on a persistent grid, {parent, node} entries two tiles
+//                        and dirty flags one tile ahead of the matrix loads, a full warp of dirty
+//                        consecutive nodes moves its 2 KiB of locals / worlds with coalesced 16-byte
+//                        accesses through a shared-memory transpose (tree_propagate.cuh) - the form
+//                        for levels large enough to be HBM bound.
+// Compiled with -fmad=false.
 #include "cull_math.cuh"
+#include "tree_propagate.cuh"
 #include "dpcu_internal.h"
 #include "dpcu_tree.h"
 
@@ -40,6 +46,45 @@ namespace dpcu
     const float4 b0 = pw[0], b1 = pw[1], b2 = pw[2], b3 = pw[3];
     world[4ull * node + r] = vecMulMat( a, b0, b1, b2, b3 );      // Tree.cpp:157, Matmnt.h:1381-1415
     if ( r == 0 ) atomicOr( dirtyWorld + ( node >> 5 ), 1u << ( node & 31u ) );   // Tree.cpp:158
+  }
+
+  constexpr int      kWideThreads    = 256;
+
+  __global__ void __launch_bounds__( kWideThreads ) treeLevelWideKernel( uint2 const *__restrict__ entries, uint32_t count,
+                                                                        float4 const *local, float4 *world,
+                                                                        uint32_t const *dirtyLocal, uint32_t *dirtyWorld )
+  {
+    __shared__ float4 sTranspose[kWideThreads / 32][2][128];     // per warp: locals in, worlds out (2 KiB each)
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * kWideThreads;
+    float4 *bufIn = sTranspose[threadIdx.x >> 5][0], *bufOut = sTranspose[threadIdx.x >> 5][1];
+    uint32_t i = blockIdx.x * kWideThreads + threadIdx.x;
+    uint2 ent = make_uint2( 0u, 0u ), entN = make_uint2( 0u, 0u );
+    if ( i < count ) ent = __ldg( entries + i );
+    if ( i + stride < count && i + stride >= i ) entN = __ldg( entries + i + stride );
+    // Tree.cpp:155 - parent bits were set by earlier launches; this launch only ORs bits of its own level
+    bool dirty = i < count && ( testBit( dirtyWorld, ent.x ) || testBit( dirtyLocal, ent.y ) );
+    const uint32_t nTiles = ( count + kWideThreads - 1 ) / kWideThreads;
+    for ( uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x, i += stride )
+    {
+      const bool     live = i < count;
+      const uint32_t iN = i + stride, iNN = iN + stride;
+      const bool     liveN = iN < count && iN >= i;
+      uint2 entNN = make_uint2( 0u, 0u );
+      if ( iNN < count && iNN >= iN && liveN ) entNN = __ldg( entries + iNN );
+      const bool dirtyN = liveN && ( testBit( dirtyWorld, entN.x ) || testBit( dirtyLocal, entN.y ) );
+      float4 w0, w1, w2, w3;
+      const uint32_t node0 = __shfl_sync( 0xffffffffu, ent.y, 0 );
+      if ( __all_sync( 0xffffffffu, live && dirty && ent.y == node0 + lane ) )
+      {
+        propagateWarpCoalesced( local, world, dirtyWorld, ent.x, node0, lane, bufIn, bufOut, w0, w1, w2, w3 );
+      }
+      else if ( live && dirty )
+      {
+        propagateNode( local, world, dirtyWorld, ent.x, ent.y, w0, w1, w2, w3 );
+      }
+      ent = entN; entN = entNN; dirty = dirtyN;
+    }
   }
 
   __global__ void treeInitNodesKernel( float4 *local, float4 *world, uint32_t *dirtyLocal, uint32_t first, uint32_t count )
@@ -104,9 +149,21 @@ namespace dpcu
     {
       uint32_t first = t->levelOffsets[l], count = t->levelOffsets[l + 1] - first;
       if ( !count ) continue;
-      treeLevelKernel<<<unsigned( divUp( size_t( count ) * 4, 256 ) ), 256, 0, s>>>(
-        static_cast<uint2 const *>( t->entries.ptr ) + first, count, static_cast<float4 const *>( t->local.ptr ),
-        static_cast<float4 *>( t->world.ptr ), static_cast<uint32_t const *>( t->dirtyLocal.ptr ), static_cast<uint32_t *>( t->dirtyWorld.ptr ) );
+      uint2 const *entries = static_cast<uint2 const *>( t->entries.ptr ) + first;
+      float4 const *local = static_cast<float4 const *>( t->local.ptr );
+      float4 *world = static_cast<float4 *>( t->world.ptr );
+      uint32_t const *dirtyLocal = static_cast<uint32_t const *>( t->dirtyLocal.ptr );
+      uint32_t *dirtyWorld = static_cast<uint32_t *>( t->dirtyWorld.ptr );
+      if ( count >= t->wideMinNodes )
+      {
+        size_t grid = divUp( size_t( count ), size_t( kWideThreads ) );
+        size_t cap  = size_t( t->smCount ) * t->wideCtasPerSm;
+        treeLevelWideKernel<<<unsigned( grid < cap ? grid : cap ), kWideThreads, 0, s>>>( entries, count, local, world, dirtyLocal, dirtyWorld );
+      }
+      else
+      {
+        treeLevelKernel<<<unsigned( divUp( size_t( count ) * 4, 256 ) ), 256, 0, s>>>( entries, count, local, world, dirtyLocal, dirtyWorld );
+      }
       DPCU_CUDA( cudaGetLastError() );
       ++t->launches;
     }
@@ -136,6 +193,10 @@ extern "C"
     dpcuTree *t = new ( std::nothrow ) dpcuTree;
     if ( !t ) return dpcu::fail( DPCU_ERR_OUT_OF_MEMORY, "dpcuTreeCreate: host allocation failed" );
     t->device = device;
+    cudaDeviceGetAttribute( &t->smCount, cudaDevAttrMultiProcessorCount, device );
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &t->wideCtasPerSm, dpcu::treeLevelWideKernel, dpcu::kWideThreads, 0 );
+    if ( t->smCount <= 0 ) t->smCount = 1;
+    if ( t->wideCtasPerSm <= 0 ) t->wideCtasPerSm = 1;
     cudaError_t e = cudaStreamCreateWithFlags( &t->stream, cudaStreamNonBlocking );
     if ( e != cudaSuccess ) { delete t; return dpcu::failCuda( e, "cudaStreamCreateWithFlags", __FILE__, __LINE__ ); }
     *out = t;
@@ -312,6 +373,17 @@ extern "C"
     DPCU_CUDA( t->done.orderBefore( t->stream ) );
     DPCU_CUDA( cudaMemcpyAsync( hostWords, t->dirtyWorld.ptr, have * 4, cudaMemcpyDeviceToHost, t->stream ) );
     DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
+    return DPCU_OK;
+  }
+
+  int dpcuTreeSetOption( dpcuTree *t, int option, size_t value )
+  {
+    DPCU_REQUIRE( t, "tree is NULL" );
+    switch ( option )
+    {
+      case DPCU_TREE_OPT_WIDE_MIN_NODES: t->wideMinNodes = value; break;
+      default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuTreeSetOption: unknown option %d", option );
+    }
     return DPCU_OK;
   }
 

@@ -14,6 +14,8 @@ struct dpcuTree
   size_t       numNodes = 0;
   size_t       numEntries = 0;
   std::vector<uint32_t> levelOffsets;
+  int          smCount = 1, wideCtasPerSm = 1;
+  size_t       wideMinNodes = size_t( 1 ) << 16;   // levels at least this large run treeLevelWideKernel
   uint64_t     launches = 0;
   uint64_t     topologyVersion = 0;   // bumped by dpcuTreeSetTopology (cached leaf bindings of cull contexts go stale)
   dpcu::StreamFence done;        // last compute submitted

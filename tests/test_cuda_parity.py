@@ -98,10 +98,13 @@ def test_lifecycle(capi, golden):
     e.close()
 
 
-def test_tree_golden(capi, golden):
+@pytest.mark.parametrize("wide_min", [None, 0])
+def test_tree_golden(capi, golden, wide_min):
     g = golden("tree")
     entries, offsets, n_nodes, local = cases.tree_case()
     t = capi.Tree(0)
+    if wide_min is not None:
+        t.set_option(capi.TREE_OPT_WIDE_MIN_NODES, wide_min)     # every level through the wide K1 form
     t.set_topology(entries, offsets, n_nodes)
     t.set_locals(0, local)
     t.compute()
@@ -367,12 +370,17 @@ def test_result_device_pointers_and_is_visible(capi, port):
 
 
 # ------------------------------------------------------------------ transform tree
-def test_tree_vs_port_large(capi, port):
+@pytest.mark.parametrize("wide_min", [None, 0, 1 << 40])
+def test_tree_vs_port_large(capi, port, wide_min):
+    """K1 in both forms: default (levels >= 65536 nodes take the persistent coalesced kernel), always
+    wide, never wide"""
     entries, offsets, n_nodes = scenes.hierarchy_topology((64, 1024, 16384, 262144))
     local = np.zeros((n_nodes, 4, 4), np.float32)
     local[0] = np.eye(4, dtype=np.float32)
     local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=0)
     t = capi.Tree(0)
+    if wide_min is not None:
+        t.set_option(capi.TREE_OPT_WIDE_MIN_NODES, wide_min)
     t.set_topology(entries, offsets, n_nodes)
     t.set_locals(0, local)
     nw = (n_nodes + 31) // 32
