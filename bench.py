@@ -282,6 +282,8 @@ def run_ours(args, rank, world, local_rank):
     if args.workload == "c3":
         entries, offsets, n_nodes = scenes.hierarchy_topology(C3_LEVELS)
         tree = capi.Tree(device)
+        if os.environ.get("DPCU_BENCH_TREE_WIDE_MIN"):          # developer A/B of the two K1 forms
+            tree.set_option(capi.TREE_OPT_WIDE_MIN_NODES, int(os.environ["DPCU_BENCH_TREE_WIDE_MIN"]))
         tree.set_topology(entries, offsets, n_nodes)
         del entries
         first_leaf = n_nodes - n_per
