@@ -214,8 +214,9 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 
 /* Tuning / reporting knobs (never change results unless stated). */
 #define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
-#define DPCU_KERNEL_AUTO    0           /* 1 view: direct; >= 2 views: view-sequential packed; lines with    */
-                                        /* peer bitsets or a host mirror                                     */
+#define DPCU_KERNEL_AUTO    0           /* the measured winner: line-granular (list built in-kernel) for large */
+                                        /* groups with 1 or >= 4 views, peer bitsets or a host mirror; else    */
+                                        /* direct (1 view) / view-sequential packed (>= 2 views)               */
 #define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */
 #define DPCU_KERNEL_STAGED  2           /* persistent CTAs, TMA bulk + cp.async staging in shared memory     */
 #define DPCU_KERNEL_VIEWS   3           /* views one after the other, packed f32x2 arithmetic                */
@@ -223,12 +224,16 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* when peer bitsets are set (dpcuCullResultSetPeerBits)             */
 #define DPCU_KERNEL_VIEWS_CHAINS 5      /* the views form with three predicate chains per axis instead of a  */
                                         /* counted compare (the earlier formulation; kept for comparison)    */
+#define DPCU_KERNEL_FUSED_LEAF   6      /* reported by DPCU_CULL_OPT_LAST_KERNEL only (dpcuCullRunWithTree)  */
 #define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */
 #define DPCU_CULL_OPT_PROFILE       5   /* 1 = bracket every cull-kernel launch with CUDA events (see below) */
 #define DPCU_CULL_OPT_FUSE_LEAF     6   /* 1 (default) = dpcuCullRunWithTree may run the tree's last level   */
                                         /* inside the cull kernel; 0 = always propagate, then cull           */
+#define DPCU_CULL_OPT_FUSE_LIST     7   /* 1 (default) = the line-granular kernel builds the changed list itself   */
+                                        /* (single-pass look-back); 0 = segment counters + compaction kernel       */
+#define DPCU_CULL_OPT_LAST_KERNEL   8   /* read-only: DPCU_KERNEL_* form the last cull ran                          */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
 /* With DPCU_CULL_OPT_PROFILE = 1: device time spent in the cull kernel (K2 only, not the memset /

@@ -17,9 +17,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF = 1, 2, 3, 4, 5, 6
+OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF, OPT_FUSE_LIST, OPT_LAST_KERNEL = 1, 2, 3, 4, 5, 6, 7, 8
 TREE_OPT_WIDE_MIN_NODES = 1
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS = 0, 1, 2, 3, 4, 5
+KERNEL_NAMES = {1: "cullDirectKernel", 2: "cullStagedKernel", 3: "cullViewsKernel", 4: "cullLinesKernel", 5: "cullViewsKernel", 6: "cullFusedLeafKernel"}
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS, KERNEL_FUSED_LEAF = 0, 1, 2, 3, 4, 5, 6
 MAX_VIEWS = 8
 
 _vp = C.c_void_p

@@ -45,6 +45,13 @@ namespace dpcu
     uint32_t *seg;       // += popc per 8192-object segment; read and zeroed again by the last CTA
     uint32_t *prefix;    // out: exclusive prefix of seg[] written by the last CTA, prefix[nSegs] = total
     uint32_t *mirror;    // optional: the result's bitset mirror in pinned host memory (line-granular kernel)
+    // changed list built inside the line-granular kernel (decoupled look-back over 1024-object chunks)
+    unsigned long long *look;   // per chunk: epoch << 34 | status << 32 | value
+    uint32_t  epoch;            // this cull's tag: entries of earlier culls read as "not there yet", no reset needed
+    uint32_t  hostCap;          // capacity of hostChanged
+    uint32_t *changed;          // out: ascending group indices
+    uint32_t *hostChanged;      // optional mirrors in pinned host memory
+    uint32_t *hostCount;
     uint32_t *peer[kMaxPeers];   // optional: full bitsets on peer GPUs (NVLink stores)
   };
 
@@ -453,16 +460,147 @@ namespace dpcu
   // over NVLink: whole lines on the wire, no barrier, no shared memory, no separate collective.
   // (Per-word 4-byte peer stores from the direct kernel were measured at 1.87 ms per 64 Mi-object
   // step on 8 GPUs; a shared-memory hand-over with two CTA barriers at 1.21 ms; the cull alone 0.98 ms.)
-  // measured at 64 Mi objects: 2 views 1.55 / 1.23 / 1.16 ms and 6 views 2.82 / 2.61 / 2.64 ms at 2 / 3 / 4 CTAs per SM
+  //
+  // kFuseList: the ordered changed list is built by this kernel as well.  Lines are claimed in
+  // ascending order from a global counter, so a line's predecessors are always in flight or done
+  // and a decoupled look-back (Merrill & Garland's single-pass scan) can hand every line the number
+  // of changes before it: a warp publishes its line's count as an AGGREGATE, walks back over its
+  // predecessors' entries 32 at a time until it meets an inclusive PREFIX, publishes its own prefix,
+  // and expands its flipped bits straight into the list - no counters, no scan, no second kernel, and
+  // with a host mirror the list crosses PCIe while the cull is still running instead of after it.
+  constexpr uint32_t kLookAggregate = 1u, kLookPrefix = 2u;
+
+  __device__ __forceinline__ unsigned long long lookPack( uint32_t epoch, uint32_t status, uint32_t value )
+  {
+    return ( static_cast<unsigned long long>( ( epoch << 2 ) | status ) << 32 ) | value;
+  }
+  __device__ __forceinline__ unsigned long long lookLoad( unsigned long long const *p )
+  {
+    unsigned long long v;
+    asm volatile( "ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"( v ) : "l"( p ) : "memory" );
+    return v;
+  }
+  __device__ __forceinline__ void lookStore( unsigned long long *p, unsigned long long v )
+  {
+    asm volatile( "st.relaxed.gpu.global.u64 [%0], %1;" :: "l"( p ), "l"( v ) : "memory" );
+  }
+
+  // exclusive prefix of line `line` (> 0): sum of the counts of lines 0 .. line-1
+  __device__ __forceinline__ uint32_t lookBack( unsigned long long const *look, uint32_t epoch, uint32_t line, uint32_t lane )
+  {
+    uint32_t excl = 0;
+    int32_t  base = int32_t( line ) - 1;                   // lane k inspects line base - k: lane 0 is the nearest predecessor
+    uint32_t polls = 0;
+    for ( ;; )
+    {
+      const int32_t idx = base - int32_t( lane );
+      unsigned long long s = idx >= 0 ? lookLoad( look + idx ) : lookPack( epoch, kLookPrefix, 0u );
+      const uint32_t tag    = uint32_t( s >> 32 );
+      const bool     valid  = ( tag >> 2 ) == epoch;
+      const bool     prefix = valid && ( tag & 3u ) == kLookPrefix;
+      const uint32_t pmask  = __ballot_sync( 0xffffffffu, prefix );
+      const uint32_t vmask  = __ballot_sync( 0xffffffffu, valid );
+      const uint32_t first  = pmask ? uint32_t( __ffs( pmask ) - 1 ) : 31u;       // nearest line that already knows its prefix
+      const uint32_t need   = first == 31u ? 0xffffffffu : ( ( 2u << first ) - 1u );
+      if ( ( vmask & need ) != need )
+      {
+        // a predecessor in the window has not published yet: it is running on some other warp; poll again
+        if ( ++polls > ( 1u << 24 ) ) __trap();            // fail loudly instead of hanging the device
+        continue;
+      }
+      uint32_t v = ( lane <= first ) ? uint32_t( s ) : 0u;
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, d );
+      excl += v;
+      if ( pmask ) return excl;
+      base -= 32;
+    }
+  }
+
+  constexpr uint32_t kNoLine = 0xffffffffu;
+
+  // Place line `line`'s changes in the list of every view: its flipped-bit words (written by this warp a
+  // line ago, read back from L2), the number of changes before it by look-back, then the expansion.
   template <int NV>
+  __device__ __forceinline__ void resolveLine( CullArgs<NV> const &a, uint32_t line, uint32_t nLines, uint32_t nWords, uint32_t lane )
+  {
+    const uint32_t myWord = ( line << 5 ) + lane;
+    __syncwarp();                                            // the warp's chg stores of that line are visible to all its lanes
+#pragma unroll 1
+    for ( int v = 0; v < NV; ++v )
+    {
+      ViewOut const &o = a.out[v];
+      uint32_t c = myWord < nWords ? __ldcg( o.chg + myWord ) : 0u;
+      const uint32_t flips = __popc( c );
+      uint32_t incl = flips;                                 // inclusive scan of the per-word counts across the line
+#pragma unroll
+      for ( int d = 1; d < 32; d <<= 1 )
+      {
+        const uint32_t t = __shfl_up_sync( 0xffffffffu, incl, d );
+        if ( lane >= d ) incl += t;
+      }
+      const uint32_t total = __shfl_sync( 0xffffffffu, incl, 31 );
+      uint32_t excl = 0;
+      if ( line > 0 )
+      {
+        excl = lookBack( o.look, o.epoch, line, lane );
+        if ( lane == 0 ) lookStore( o.look + line, lookPack( o.epoch, kLookPrefix, excl + total ) );
+      }
+      // expand: word l's flipped bits go to list[excl + (changes in words 0..l-1) ...], ascending
+      uint32_t off = excl + incl - flips;
+      const uint32_t base = myWord << 5;
+      while ( c )
+      {
+        o.changed[off++] = base + uint32_t( __ffs( c ) - 1 );
+        c &= c - 1;
+      }
+      if ( o.hostChanged )
+      {
+        // the line's run again as coalesced stores into the pinned host mirror (the entries just written
+        // are in L2; __syncwarp orders the warp's writes before its reads)
+        __syncwarp();
+        for ( uint32_t k = lane; k < total; k += 32 )
+        {
+          if ( excl + k < o.hostCap ) o.hostChanged[excl + k] = __ldcg( o.changed + excl + k );
+        }
+      }
+      if ( line == nLines - 1 && lane == 0 )
+      {
+        o.prefix[a.nSegs] = excl + total;                    // where the compaction path keeps the length of the list
+        if ( o.hostCount ) *o.hostCount = excl + total;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void rearmInLastCta( uint32_t *done )
+  {
+    __shared__ uint32_t sLastLines;
+    __syncthreads();
+    if ( threadIdx.x == 0 ) sLastLines = ( atomicAdd( done, 1u ) == gridDim.x - 1 ) ? 1u : 0u;
+    __syncthreads();
+    if ( sLastLines && threadIdx.x == 0 ) done[0] = done[1] = 0u;      // ticket and line counter: ready for the next cull
+  }
+
+  // measured at 64 Mi objects: 2 views 1.55 / 1.23 / 1.16 ms and 6 views 2.82 / 2.61 / 2.64 ms at 2 / 3 / 4 CTAs per SM
+  template <int NV, bool kFuseList>
   __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : ( NV <= 3 ? 4 : 3 ) )
   cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane   = threadIdx.x & 31u;
     const uint32_t nWords = ( a.n + 31u ) >> 5, nLines = ( nWords + 31u ) >> 5;
     const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
-    for ( uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 ); line < nLines; line += nWarps )
+    uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 );
+    uint32_t pending = kNoLine;
+    for ( ;; )
     {
+      if ( kFuseList )
+      {
+        // ascending claims: every predecessor of a claimed line belongs to a warp that is already running
+        uint32_t claimed = 0;
+        if ( lane == 0 ) claimed = atomicAdd( a.chunkCounter, 1u );
+        line = __shfl_sync( 0xffffffffu, claimed, 0 );
+      }
+      if ( line >= nLines ) break;
       const uint32_t word0 = line << 5, myWord = word0 + lane;
       const bool     wordLive = myWord < nWords;
       uint32_t old[NV], acc[NV];
@@ -530,15 +668,33 @@ namespace dpcu
             flips = __popc( c );
           }
         }
-        if ( a.buildChanged )
+        if ( a.buildChanged && !kFuseList )
         {
 #pragma unroll
           for ( int d = 16; d > 0; d >>= 1 ) flips += __shfl_xor_sync( 0xffffffffu, flips, d );
           if ( lane == 0 && flips ) atomicAdd( o.seg + ( word0 >> ( kSegObjectsLog2 - 5 ) ), flips );
         }
+        if ( a.buildChanged && kFuseList )
+        {
+          // publish this line's count right away; its place in the list is resolved one line later (below)
+#pragma unroll
+          for ( int d = 16; d > 0; d >>= 1 ) flips += __shfl_xor_sync( 0xffffffffu, flips, d );
+          if ( lane == 0 ) lookStore( o.look + line, lookPack( o.epoch, line == 0 ? kLookPrefix : kLookAggregate, flips ) );
+        }
       }
+      if ( kFuseList && a.buildChanged )
+      {
+        // The look-back of the PREVIOUS line runs now, a whole line of work after its count was published:
+        // by then its predecessors have published theirs and the walk does not wait (resolving a line
+        // immediately made every warp wait for its slowest recent predecessor: 1.11 ms instead of 1.01 ms).
+        if ( pending != kNoLine ) resolveLine<NV>( a, pending, nLines, nWords, lane );
+        pending = line;
+      }
+      if ( !kFuseList ) line += nWarps;
     }
-    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+    if ( kFuseList && a.buildChanged && pending != kNoLine ) resolveLine<NV>( a, pending, nLines, nWords, lane );
+    if ( kFuseList ) rearmInLastCta( a.done );
+    else if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
 
   // ------------------------------------------------------------------------------------------
@@ -970,6 +1126,9 @@ struct dpcuCullResult
   size_t   peerWordOffset = 0;
   dpcuCullResult *next = nullptr, *prev = nullptr;
 
+  dpcu::DeviceArray look;                           // look-back entries of the fused list, one per 1024 objects
+  size_t   lookCap = 0;
+  uint32_t lookEpoch = 0;
   dpcu::DeviceArray visible, visCounters;           // dpcuCullResultBuildVisibleList: indices | done[4], seg[cap], prefix[cap]
   size_t   visSegsCap = 0, visSegs = 0;
   bool     visBuilt = false;
@@ -997,7 +1156,8 @@ struct dpcuCull
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1;
+  int          lastKernel = 0;           // DPCU_KERNEL_* of the last cull launched (DPCU_CULL_OPT_LAST_KERNEL)
   uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
   dpcuTree    *leafTree = nullptr;       // cached answer of the leaf-binding check of dpcuCullRunWithTree
   uint64_t     leafTopologyVersion = 0, leafObjectsVersion = 0;
@@ -1057,6 +1217,14 @@ namespace dpcu
       if ( r->nPeers == 0 ) { /* local only */ }
     }
     if ( ctx->optChanged ) DPCU_TRY( r->changed.reserve( ( n ? n : 1 ) * 4, false, stream ) );
+    size_t nLines = divUp( divUp( n, 32 ), 32 );
+    if ( ctx->optChanged && nLines > r->lookCap )
+    {
+      DPCU_TRY( r->look.reserve( ( nLines + nLines / 2 + 64 ) * 8, false, stream ) );
+      DPCU_CUDA( cudaMemsetAsync( r->look.ptr, 0, r->look.capacity, stream ) );
+      r->lookCap = r->look.capacity / 8;
+      r->lookEpoch = 0;
+    }
     if ( nSegs + 1 > r->nSegsCap )
     {
       size_t cap = nSegs + 1 + nSegs / 2;
@@ -1071,7 +1239,7 @@ namespace dpcu
 
   template <int NV>
   static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf,
-                         bool *mirrorsWritten )
+                         bool *mirrorsWritten, bool *listBuilt )
   {
     CullArgs<NV> args;
     memset( &args, 0, sizeof args );
@@ -1102,12 +1270,37 @@ namespace dpcu
     const bool peers     = args.nPeers > 0;
     bool mirrors = false;
     for ( int v = 0; v < NV; ++v ) mirrors = mirrors || results[v]->dBits != nullptr;
-    // whole 128-byte lines are what NVLink peers and PCIe host mirrors want to see: both select the line-granular
-    // form.  A warp per 1024 objects needs a few million objects to fill the machine; below that the mirror is
-    // served by a copy queued behind the kernel (measured at 1 Mi objects: 86 us per step in-kernel, 79 us copied).
-    const bool mirrorLines = mirrors && !leaf && ctx->optKernel == DPCU_KERNEL_AUTO && ctx->n >= size_t( ctx->smCount ) * 32u * 1024u;
-    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || mirrorLines );
+    // Whole 128-byte lines are what NVLink peers and PCIe host mirrors want to see, and the line-granular form
+    // builds the changed list in the same pass (no compaction kernel): measured at 64 Mi objects, step time with
+    // an ordered changed list, lines vs the alternative - 1 view 1.009 vs 1.021 ms (direct + compaction), 6 views
+    // 2.631 vs 2.643 ms (views + compaction), 2 views 1.16 vs 1.14 ms.  A warp per 1024 objects needs a few
+    // million objects to fill the machine; below that AUTO stays with one thread per object (and serves a host
+    // mirror by a copy queued behind the kernel: 86 us per step in-kernel vs 79 us copied at 1 Mi objects).
+    const bool bigEnough = ctx->n >= size_t( ctx->smCount ) * 32u * 1024u;
+    const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
+                        && ( mirrors || ( ctx->optChanged && ctx->optFuseList && ( NV == 1 || NV >= 4 ) ) );
+    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || autoLines );
     *mirrorsWritten = useLines && !leaf;
+    const bool fuseList = useLines && !leaf && ctx->optChanged && ctx->optFuseList;
+    *listBuilt = fuseList;
+    if ( fuseList )
+    {
+      for ( int v = 0; v < NV; ++v )
+      {
+        dpcuCullResult *r = results[v];
+        if ( ++r->lookEpoch >= ( 1u << 30 ) )
+        {
+          DPCU_CUDA( cudaMemsetAsync( r->look.ptr, 0, r->look.capacity, stream ) );     // tags wrap: start over
+          r->lookEpoch = 1;
+        }
+        args.out[v].look        = static_cast<unsigned long long *>( r->look.ptr );
+        args.out[v].epoch       = r->lookEpoch;
+        args.out[v].changed     = static_cast<uint32_t *>( r->changed.ptr );
+        args.out[v].hostChanged = r->dChanged;
+        args.out[v].hostCount   = r->dCount;
+        args.out[v].hostCap     = uint32_t( r->hChangedCap < 0xffffffffull ? r->hChangedCap : 0xffffffffull );
+      }
+    }
     if ( peers && ( ctx->optFma || leaf ) )
       return fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: peer bitsets are served by the line-granular kernel only (not the FMA or fused-leaf forms)" );
     const bool useFused  = leaf != nullptr;
@@ -1131,7 +1324,8 @@ namespace dpcu
     if ( perSm <= 0 )
     {
       if ( useFused ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullFusedLeafKernel<NV>, kCullThreads, 0 );
-      else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV>, kCullThreads, 0 );
+      else if ( useLines && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, true>, kCullThreads, 0 );
+      else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, false>, kCullThreads, 0 );
       else if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
       else if ( useStaged ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullStagedKernel<NV>, kCullThreads, stagedSmem );
       else if ( useViews && useChains ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV, false>, kCullThreads, 0 );
@@ -1172,7 +1366,8 @@ namespace dpcu
       const uint32_t nLines = uint32_t( divUp( divUp( ctx->n, 32 ), 32 ) );
       const uint32_t ctasForLines = uint32_t( divUp( nLines, kCullThreads / 32 ) );
       if ( uint32_t( grid ) > ctasForLines ) grid = int( ctasForLines );
-      cullLinesKernel<NV><<<grid, kCullThreads, 0, stream>>>( args );
+      if ( fuseList ) cullLinesKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
+      else            cullLinesKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
     }
     else if ( ctx->optFma )
@@ -1197,6 +1392,8 @@ namespace dpcu
     }
     if ( evStop ) DPCU_CUDA( cudaEventRecord( evStop, stream ) );
     ++ctx->launches;
+    ctx->lastKernel = useFused ? DPCU_KERNEL_FUSED_LEAF : useLines ? DPCU_KERNEL_LINES : ctx->optFma ? DPCU_KERNEL_DIRECT
+                    : useStaged ? DPCU_KERNEL_STAGED : useViews ? ( useChains ? DPCU_KERNEL_VIEWS_CHAINS : DPCU_KERNEL_VIEWS ) : DPCU_KERNEL_DIRECT;
     return DPCU_OK;
   }
 }
@@ -1416,7 +1613,7 @@ extern "C"
     r->done.hostWait();
     r->done.destroy();
     r->bits.release(); r->chg.release(); r->changed.release(); r->counters.release();
-    r->visible.release(); r->visCounters.release();
+    r->visible.release(); r->visCounters.release(); r->look.release();
     if ( r->prev ) r->prev->next = r->next; else ctx->results = r->next;
     if ( r->next ) r->next->prev = r->prev;
     delete r;
@@ -1480,20 +1677,20 @@ extern "C"
       return DPCU_OK;
     }
     int rc = DPCU_OK;
-    bool mirrorsWritten = false;
+    bool mirrorsWritten = false, listBuilt = false;
     switch ( nViews )
     {
-      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
-      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf, &mirrorsWritten ); break;
+      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
     }
     DPCU_TRY( rc );
-    if ( ctx->optChanged )
+    if ( ctx->optChanged && !listBuilt )
     {
       dpcu::CompactArgs ca;
       memset( &ca, 0, sizeof ca );
@@ -1875,6 +2072,7 @@ extern "C"
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;
       case DPCU_CULL_OPT_PROFILE:      ctx->optProfile = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FUSE_LEAF:    ctx->optFuseLeaf = value ? 1 : 0; break;
+      case DPCU_CULL_OPT_FUSE_LIST:    ctx->optFuseList = value ? 1 : 0; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -1891,6 +2089,8 @@ extern "C"
       case DPCU_CULL_OPT_CTAS_PER_SM:  *value = ctx->optCtasPerSm; break;
       case DPCU_CULL_OPT_PROFILE:      *value = ctx->optProfile; break;
       case DPCU_CULL_OPT_FUSE_LEAF:    *value = ctx->optFuseLeaf; break;
+      case DPCU_CULL_OPT_FUSE_LIST:    *value = ctx->optFuseList; break;
+      case DPCU_CULL_OPT_LAST_KERNEL:  *value = ctx->lastKernel; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
     return DPCU_OK;

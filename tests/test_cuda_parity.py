@@ -205,7 +205,16 @@ def test_multi_view_equals_single_views(capi, port):
 
 
 # ------------------------------------------------------------------ both exact kernel forms, 1..8 views
-KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5}
+# every exact form of K2: DPCU_KERNEL_* plus, for the line-granular kernel, how the changed list is built
+# (inside the kernel by single-pass look-back, the default, or by segment counters + the compaction kernel)
+KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4}
+
+
+def _select_kernel(capi, ctx, kernel):
+    ctx.set_option(capi.OPT_KERNEL, dict(KERNELS, auto=0)[kernel])
+    if kernel.endswith("_compact"):
+        ctx.set_option(capi.OPT_FUSE_LIST, 0)
+
 
 
 def _views_for(nv, extra=()):
@@ -217,7 +226,7 @@ def _views_for(nv, extra=()):
 def _check_views(capi, port, kernel, lower4, extent4, tidx, mats, vps, frames=1):
     n = len(lower4)
     ctx = capi.Cull(0)
-    ctx.set_option(capi.OPT_KERNEL, KERNELS[kernel])
+    _select_kernel(capi, ctx, kernel)
     ctx.set_objects(lower4, extent4, tidx)
     ctx.set_matrices(mats.reshape(-1))
     res = [ctx.result_create() for _ in range(len(vps))]
@@ -590,7 +599,7 @@ class _Mirror:
             b.close()
 
 
-@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines"])
+@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact"])
 @pytest.mark.parametrize("nv", [1, 3])
 def test_host_mirror_matches_port(capi, port, kernel, nv):
     """dpcuCullResultSetHostMirror: after run + synchronize the pinned buffers hold exactly what
@@ -600,7 +609,7 @@ def test_host_mirror_matches_port(capi, port, kernel, nv):
     n = 1024 * 21 + 777
     lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C2)
     ctx = capi.Cull(0)
-    ctx.set_option(capi.OPT_KERNEL, dict(KERNELS, auto=0)[kernel])
+    _select_kernel(capi, ctx, kernel)
     ctx.set_objects(lower4, extent4, tidx)
     ctx.set_matrices(mats.reshape(-1))
     res = [ctx.result_create() for _ in range(nv)]

@@ -108,12 +108,19 @@ def test_c4_sixty_four_million_single_view(capi, port, n):
     assert np.array_equal(r.visible(), _set_bits(old, n))
     # every kernel form yields the same words at full size
     crc = zlib.crc32(old.tobytes())
+    hidden = _set_bits(~old, n)
     for kernel in (capi.KERNEL_DIRECT, capi.KERNEL_VIEWS, capi.KERNEL_LINES, capi.KERNEL_STAGED):
         sc.ctx.set_option(capi.OPT_KERNEL, kernel)
         r2 = sc.ctx.result_create()
         sc.ctx.run([r2], scenes.orbit_camera(5))
         assert zlib.crc32(r2.bits().tobytes()) == crc, "kernel form %d" % kernel
         assert r2.changed_count() == n - _popcount(old)          # first cull of a result: the invisible set
+        if kernel == capi.KERNEL_LINES:
+            # the list built inside the kernel (look-back over 65 536 lines): first cull = every hidden object
+            # (58 M entries), then a moved camera = the ascending flips
+            assert np.array_equal(r2.changed(), hidden)
+            sc.ctx.run([r2], scenes.orbit_camera(9))
+            _check_changed(old, r2.bits(), r2.changed(), n)
         r2.close()
     r.close()
     sc.close()
