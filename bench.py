@@ -603,7 +603,7 @@ def run_ours(args, rank, world, local_rank):
                 "mirror_equals_device_result": e2e_checked,
                 "what": "camera from pinned host memory in, visibility bitset + changed list into pinned host memory out, "
                         "through dpcuCullRun / dpcuCullResultSynchronize with a host mirror (dpcuCullResultSetHostMirror): "
-                        "PCIe stores from the cull and compaction kernels, no copy after the cull"},
+                        "the cull kernel stores bitset lines and changed-list runs over PCIe while it runs, no copy after the cull"},
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
     }
