@@ -233,6 +233,9 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* inside the cull kernel; 0 = always propagate, then cull           */
 #define DPCU_CULL_OPT_FUSE_LIST     7   /* 1 (default) = the line-granular kernel builds the changed list itself   */
                                         /* (single-pass look-back); 0 = segment counters + compaction kernel       */
+#define DPCU_CULL_OPT_FILTER        9   /* 1 (default) = multi-view culls decide provable (object, view) pairs from  */
+                                        /* the OBB's centre and radius and run the reference arithmetic only on the  */
+                                        /* rest (same bits, proof in cull_filter.cuh); 0 = reference arithmetic for all */
 #define DPCU_CULL_OPT_LAST_KERNEL   8   /* read-only: DPCU_KERNEL_* form the last cull ran                          */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
@@ -240,6 +243,12 @@ int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
  * compaction around it) since the last call, measured with CUDA events on the launching stream;
  * synchronises those events and resets the accumulator.  This is the number bench.py's roofline uses. */
 int dpcuCullGetKernelTime(dpcuCull *ctx, double *totalMs, uint64_t *launches);
+/* Diagnostics for tests/test_sass.py (no device needed): byte offsets, inside the cull kernels' parameter block
+ * for nViews views, of the (1.0f, 1.0f) multiplier, the view-projection rows and the filter constants, so that the
+ * SASS check can tell the reference arithmetic (products of view-projection entries must never be contracted into
+ * a fused multiply-add) from the filter's own arithmetic (any rounding is fine there). */
+int dpcuDebugKernelArgLayout(int nViews, size_t *onePairOffset, size_t *viewProjectionOffset, size_t *filterOffset,
+                             size_t *totalBytes);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int dpcuCullGetLaunchCount(const dpcuCull *ctx, uint64_t *launches);
 

@@ -1,0 +1,184 @@
+// Multi-view cull with an exact-by-construction filter in front of the reference arithmetic.
+//
+// cull_views.cuh evaluates the reference's eight-corner test for every (object, view) pair:
+// ~160 warp instructions per pair, which makes a six-view cull issue bound at 0.4 of the HBM
+// roofline.  Almost every pair is far from the frustum boundary, where the outcome can be PROVEN
+// from the OBB's centre and radius with a few instructions; only the pairs that are not provable
+// run the reference arithmetic.  The proof obligations (this is what keeps the result bit-exact):
+//
+//   The reference (dp/culling/cpu/src/ManagerImpl.cpp:199-289) computes, in binary32, the clip
+//   coordinates (x_j, y_j, z_j, w_j) of the eight corners j of the OBB {p; a, b, c} and sets, per
+//   axis, out-code bit N when x_j <= -w_j, else bit P when w_j <= x_j; the object is invisible
+//   iff some bit is set for all eight corners.  For finite operands
+//        x <= -w   <=>   x + w <= 0      and      w <= x   <=>   w - x <= 0      (real sums)
+//   so with the plane functions  fN = x + w,  fP = w - x  (linear in the corner):
+//     (V) if the real value of every plane function at the box centre exceeds the rounding error E
+//         of the reference's corner computation, then for every plane SOME float corner has
+//         f_j > 0 (the centre is the mean of the corners), i.e. no out-code bit survives all
+//         corners: visible;
+//     (N) if  fN(centre) + support_N < -E  every float corner has x_j + w_j < 0: bit N everywhere,
+//         invisible;
+//     (P) if  fP(centre) + support_P < -E  and  fN(centre) - support_N > E  every corner has
+//         w_j <= x_j and not x_j <= -w_j: bit P everywhere, invisible.
+//   E: the reference forms every clip coordinate from at most 8 rounded operations on terms whose
+//   absolute values sum to at most  S = sum_r (|p_r| + |a_r| + |b_r| + |c_r|) * sum_c |P[r][c]|,
+//   so its error is below 8u S / (1 - 8u), u = 2^-24; the filter's own centre / plane / support
+//   arithmetic adds less than another 8u S.  The margin used is 2^-17 S (8x that sum); supports
+//   are bounded by Cauchy-Schwarz with radius and plane norms rounded up.  A decision is taken
+//   only when a comparison is TRUE, so NaN never decides, and only when S < 2^96 (nothing
+//   overflowed).  Everything else - and every warp that holds a non-affine object or a
+//   non-finite view-projection - takes the reference arithmetic of cull_views.cuh.
+//
+// The undecided pairs of a warp's 32 objects x NV views are gathered into dense batches of 32
+// (pair -> lane), their OBBs fetched with shuffles and their view-projection rows from a small
+// shared-memory table, evaluated with the exact packed arithmetic, and scattered back into the
+// per-view ballot words with warp OR-reductions.
+#pragma once
+
+#include "cull_views.cuh"
+
+namespace dpcu
+{
+  // per view, computed on the host in double precision from the view-projection (see makeViewFilter)
+  struct ViewFilter
+  {
+    float2 nx[3], ny[3], nz[3], nw[3];   // plane functions per axis (x, y, z): .x = N plane (col_a + col_w), .y = P plane (col_w - col_a)
+    float2 rho[3];                       // |plane.xyz|_2, rounded up
+    float4 q;                            // 2^-17 * sum_c |P[r][c]| per row r: margin = q . (aw, 1)
+  };
+
+  __device__ __forceinline__ f32x2 fma2( f32x2 a, f32x2 b, f32x2 c )
+  {
+    f32x2 r;
+    asm( "fma.rn.f32x2 %0, %1, %2, %3;" : "=l"( r ) : "l"( a ), "l"( b ), "l"( c ) );
+    return r;
+  }
+  __device__ __forceinline__ f32x2 asPair( float2 v )
+  {
+    return pack2( v.x, v.y );
+  }
+
+  __device__ __forceinline__ float sqrtApprox( float x )
+  {
+    float r;
+    asm( "sqrt.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) );    // relative error < 2^-22, flushed inputs are covered by the radius slack
+    return r;
+  }
+
+  // what the filter needs of an object, once for all views
+  struct ObbSphere
+  {
+    float cx, cy, cz;      // centre
+    float r;               // >= half diagonal
+    float awx, awy, awz;   // |p| + |a| + |b| + |c| per component
+  };
+
+  __device__ __forceinline__ ObbSphere makeSphere( Obb const &o )
+  {
+    ObbSphere s;
+    s.cx = o.pt.x + 0.5f * ( ( o.ax.x + o.ay.x ) + o.az.x );
+    s.cy = o.pt.y + 0.5f * ( ( o.ax.y + o.ay.y ) + o.az.y );
+    s.cz = o.pt.z + 0.5f * ( ( o.ax.z + o.ay.z ) + o.az.z );
+    const float la = sqrtApprox( o.ax.x * o.ax.x + o.ax.y * o.ax.y + o.ax.z * o.ax.z );
+    const float lb = sqrtApprox( o.ay.x * o.ay.x + o.ay.y * o.ay.y + o.ay.z * o.ay.z );
+    const float lc = sqrtApprox( o.az.x * o.az.x + o.az.y * o.az.y + o.az.z * o.az.z );
+    // 0.5 * (1 + 2^-20): rounded up past the sqrt / add errors; 2^-60: components whose squares underflowed
+    s.r   = ( ( la + lb ) + lc ) * 0.50000048f + 8.7e-19f;
+    s.awx = ( fabsf( o.pt.x ) + fabsf( o.ax.x ) ) + ( fabsf( o.ay.x ) + fabsf( o.az.x ) );
+    s.awy = ( fabsf( o.pt.y ) + fabsf( o.ax.y ) ) + ( fabsf( o.ay.y ) + fabsf( o.az.y ) );
+    s.awz = ( fabsf( o.pt.z ) + fabsf( o.ax.z ) ) + ( fabsf( o.ay.z ) + fabsf( o.az.z ) );
+    return s;
+  }
+
+  // (V), (N), (P) above for one view: visible / invisible proven, or neither
+  __device__ __forceinline__ void classify( ObbSphere const &s, ViewFilter const &f, bool &visible, bool &invisible )
+  {
+    const f32x2 cx = pack2( s.cx, s.cx ), cy = pack2( s.cy, s.cy ), cz = pack2( s.cz, s.cz ), rr = pack2( s.r, s.r );
+    const float m = fmaf( s.awx, f.q.x, fmaf( s.awy, f.q.y, fmaf( s.awz, f.q.z, f.q.w ) ) );
+    const float nm = -m;
+    const bool sane = m < 6.0e23f;                         // S < 2^96 (q carries the 2^-17): nothing overflowed; false for NaN
+    float fmin = 3.0e38f, hNmin = 3.0e38f;
+    bool invP = false;
+#pragma unroll
+    for ( int a = 0; a < 3; ++a )
+    {
+      const f32x2 F = fma2( cx, asPair( f.nx[a] ), fma2( cy, asPair( f.ny[a] ), fma2( cz, asPair( f.nz[a] ), asPair( f.nw[a] ) ) ) );
+      const f32x2 H = fma2( rr, asPair( f.rho[a] ), F );   // centre value + support
+      float fN, fP, hN, hP;
+      unpack2( F, fN, fP );
+      unpack2( H, hN, hP );
+      const float lN = fmaf( -s.r, f.rho[a].x, fN );       // centre value - support (N plane)
+      fmin  = fminf( fmin, fminf( fN, fP ) );              // NaN operands drop out of fminf: guarded by `sane` below
+      hNmin = fminf( hNmin, hN );
+      invP  = invP | ( ( hP < nm ) & ( lN > m ) );
+    }
+    // every value that entered a min is finite when m is (|value| <= S): NaN cannot hide behind fminf
+    visible   = sane & ( fmin > m );
+    invisible = sane & !visible & ( ( hNmin < nm ) | invP );
+  }
+
+  // All NV views of the warp's 32 objects; every lane's object is affine and the view-projections are
+  // finite (the caller checked).  sP: the views' rows as ViewPairs in shared memory (8 x f32x2 per view);
+  // scratch: shared memory private to the warp.
+  // Returns, in lane v, the ballot word of view v - the contract of cullViews.
+  template <int NV>
+  struct FilterScratch
+  {
+    float4  obb[3][32];        // the 32 OBBs (12 floats each: pt.xyz, ax.xyz, ay.xyz, az.xyz), parked here for the undecided pairs
+    uint8_t slots[32 * NV];    // undecided pairs in (view, lane) order: view << 5 | lane
+  };
+
+  template <int NV>
+  __device__ __forceinline__ uint32_t cullViewsFiltered( Obb const &obb, ViewFilter const ( &vf )[NV], f32x2 const *sP, FilterScratch<NV> &scratch,
+                                                         f32x2 one, bool live, uint32_t lane )
+  {
+    const ObbSphere s = makeSphere( obb );
+    const uint32_t below = ( 1u << lane ) - 1u;
+    uint32_t myWord = 0, total = 0;                        // lane v: decided-visible ballot of view v; undecided pairs so far
+    uint8_t *slots = scratch.slots;
+    __syncwarp();                                          // the previous call's scratch reads are done
+    // the OBB leaves the registers here: only centre, radius and the error scale stay live across the views
+    scratch.obb[0][lane] = make_float4( obb.pt.x, obb.pt.y, obb.pt.z, obb.ax.x );
+    scratch.obb[1][lane] = make_float4( obb.ax.y, obb.ax.z, obb.ay.x, obb.ay.y );
+    scratch.obb[2][lane] = make_float4( obb.ay.z, obb.az.x, obb.az.y, obb.az.z );
+#pragma unroll
+    for ( int v = 0; v < NV; ++v )
+    {
+      bool vis, inv;
+      classify( s, vf[v], vis, inv );
+      const bool open = live & !vis & !inv;
+      const uint32_t bv = __ballot_sync( 0xffffffffu, vis & live );
+      const uint32_t bo = __ballot_sync( 0xffffffffu, open );
+      if ( lane == uint32_t( v ) ) myWord = bv;
+      // undecided pairs queue up in (view, lane) order: slot -> (view, lane that owns the object)
+      if ( open ) slots[total + __popc( bo & below )] = uint8_t( ( v << 5 ) | lane );
+      total += __popc( bo );
+    }
+    __syncwarp();
+    for ( uint32_t base = 0; base < total; base += 32 )
+    {
+      const bool     mine = base + lane < total;
+      const uint32_t slot = mine ? slots[base + lane] : 0u;
+      const uint32_t view = slot >> 5, src = slot & 31u;
+      // the pair's OBB, parked by the lane that owns the object (affine: pt.w == 1, a.w == b.w == c.w == 0)
+      const float4 o0 = scratch.obb[0][src], o1 = scratch.obb[1][src], o2 = scratch.obb[2][src];
+      Obb o;
+      o.pt = make_float4( o0.x, o0.y, o0.z, 1.0f );
+      o.ax = make_float4( o0.w, o1.x, o1.y, 0.0f );
+      o.ay = make_float4( o1.z, o1.w, o2.x, 0.0f );
+      o.az = make_float4( o2.y, o2.z, o2.w, 0.0f );
+      ViewPairs P;
+#pragma unroll
+      for ( int k = 0; k < 8; ++k ) P.p[k] = sP[view * 8 + k];
+      const bool visible = cornersVisible<true>( clipVectors<true>( broadcastObb( o ), P, one ) );
+      const uint32_t bit = ( mine && visible ) ? ( 1u << src ) : 0u;
+#pragma unroll
+      for ( int u = 0; u < NV; ++u )
+      {
+        const uint32_t m = __reduce_or_sync( 0xffffffffu, view == uint32_t( u ) ? bit : 0u );
+        if ( lane == uint32_t( u ) ) myWord |= m;
+      }
+    }
+    return myWord;
+  }
+}

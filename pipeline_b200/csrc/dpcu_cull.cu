@@ -24,10 +24,12 @@
 #include "cull_math.cuh"
 #include "cull_stage.cuh"
 #include "cull_views.cuh"
+#include "cull_filter.cuh"
 #include "tree_propagate.cuh"
 #include "dpcu_internal.h"
 #include "dpcu_tree.h"
 
+#include <cstddef>
 #include <new>
 #include <vector>
 
@@ -71,9 +73,20 @@ namespace dpcu
     uint32_t     *chunkCounter;   // staged kernel: next unclaimed chunk of kChunkTiles tiles
     int           vpFinite;  // every view-projection entry is finite (enables the affine shortcut of cull_views.cuh)
     unsigned long long onePair;   // (1.0f, 1.0f): runtime multiplier of cull_views.cuh::addProd
+    int           useFilter; // cull_filter.cuh: decide provable (object, view) pairs from centre and radius
     ViewOut       out[NV];
     float4        vp[NV][4];
+    ViewFilter    filter[NV];
   };
+
+  // the views' rows as packed pairs in shared memory, for lanes that evaluate different views (cull_filter.cuh)
+  template <int NV>
+  __device__ __forceinline__ void fillViewTable( f32x2 *sP, CullArgs<NV> const &a )
+  {
+    f32x2 const *src = reinterpret_cast<f32x2 const *>( &a.vp[0][0] );
+    for ( uint32_t k = threadIdx.x; k < NV * 8u; k += blockDim.x ) sP[k] = src[k];
+    __syncthreads();
+  }
 
 #ifndef DPCU_FMA_VARIANT
 #define DPCU_KERNEL_NAME( name ) name
@@ -220,6 +233,9 @@ namespace dpcu
   cullViewsKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane = threadIdx.x & 31u;
+    __shared__ f32x2 sP[NV * 8];
+    __shared__ FilterScratch<NV> sScratch[kCullThreads / 32];
+    fillViewTable<NV>( sP, a );
 #if DPCU_VIEWS_PREFETCH
     // Two dependent DRAM round trips (object -> its matrix) head every tile and this kernel runs at
     // 8 warps per scheduler at most, so a third of the warp time was spent waiting on them (ncu:
@@ -270,9 +286,16 @@ namespace dpcu
       }
       const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
       const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
-      const ObbPairs ob = broadcastObb( obb );
-
-      const uint32_t myWord = fast ? cullViews<NV, true, kCount>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false, kCount>( ob, a.vp, a.onePair, live, lane );
+      uint32_t myWord;
+      if ( fast && a.useFilter && kCount )
+      {
+        myWord = cullViewsFiltered<NV>( obb, a.filter, sP, sScratch[threadIdx.x >> 5], a.onePair, live, lane );
+      }
+      else
+      {
+        const ObbPairs ob = broadcastObb( obb );
+        myWord = fast ? cullViews<NV, true, kCount>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false, kCount>( ob, a.vp, a.onePair, live, lane );
+      }
 
       if ( lane < NV && wordLive )
       {
@@ -591,6 +614,9 @@ namespace dpcu
     const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
     uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 );
     uint32_t pending = kNoLine;
+    __shared__ f32x2 sP[NV * 8];
+    __shared__ FilterScratch<NV> sScratch[kCullThreads / 32];
+    if ( NV > 1 ) fillViewTable<NV>( sP, a );
     for ( ;; )
     {
       if ( kFuseList )
@@ -638,8 +664,16 @@ namespace dpcu
         {
           const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
           const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
-          const ObbPairs ob = broadcastObb( obb );
-          const uint32_t perView = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+          uint32_t perView;
+          if ( fast && a.useFilter )
+          {
+            perView = cullViewsFiltered<NV>( obb, a.filter, sP, sScratch[threadIdx.x >> 5], a.onePair, live, lane );
+          }
+          else
+          {
+            const ObbPairs ob = broadcastObb( obb );
+            perView = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+          }
 #pragma unroll
           for ( int v = 0; v < NV; ++v )
           {
@@ -1156,7 +1190,7 @@ struct dpcuCull
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1;
   int          lastKernel = 0;           // DPCU_KERNEL_* of the last cull launched (DPCU_CULL_OPT_LAST_KERNEL)
   uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
   dpcuTree    *leafTree = nullptr;       // cached answer of the leaf-binding check of dpcuCullRunWithTree
@@ -1237,6 +1271,38 @@ namespace dpcu
     return DPCU_OK;
   }
 
+  // ViewFilter of one view-projection (row-major, row-vector convention), in double precision; every bound is
+  // rounded towards "less decisive" (cull_filter.cuh)
+  static float roundUp( double x )
+  {
+    float f = static_cast<float>( x );
+    return ( static_cast<double>( f ) < x ) ? nextafterf( f, INFINITY ) : f;
+  }
+  static void makeViewFilter( float const *vp, ViewFilter &f )
+  {
+    double P[4][4];
+    for ( int r = 0; r < 4; ++r ) for ( int c = 0; c < 4; ++c ) P[r][c] = vp[4 * r + c];
+    for ( int a = 0; a < 3; ++a )
+    {
+      double n[2][4];
+      for ( int r = 0; r < 4; ++r )
+      {
+        n[0][r] = P[r][a] + P[r][3];        // N plane: x + w
+        n[1][r] = P[r][3] - P[r][a];        // P plane: w - x
+      }
+      f.nx[a] = make_float2( float( n[0][0] ), float( n[1][0] ) );
+      f.ny[a] = make_float2( float( n[0][1] ), float( n[1][1] ) );
+      f.nz[a] = make_float2( float( n[0][2] ), float( n[1][2] ) );
+      f.nw[a] = make_float2( float( n[0][3] ), float( n[1][3] ) );
+      const double inflate = 1.0 + 1.0 / 1048576.0;
+      f.rho[a] = make_float2( roundUp( sqrt( n[0][0] * n[0][0] + n[0][1] * n[0][1] + n[0][2] * n[0][2] ) * inflate ),
+                              roundUp( sqrt( n[1][0] * n[1][0] + n[1][1] * n[1][1] + n[1][2] * n[1][2] ) * inflate ) );
+    }
+    double q[4];
+    for ( int r = 0; r < 4; ++r ) q[r] = ( fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] ) ) / 131072.0;
+    f.q = make_float4( roundUp( q[0] ), roundUp( q[1] ), roundUp( q[2] ), roundUp( q[3] ) );
+  }
+
   template <int NV>
   static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf,
                          bool *mirrorsWritten, bool *listBuilt )
@@ -1264,7 +1330,9 @@ namespace dpcu
       if ( uint32_t( r->nPeers ) > args.nPeers ) args.nPeers = uint32_t( r->nPeers );
       args.peerWordOffset = uint32_t( r->peerWordOffset );
       memcpy( args.vp[v], vps + 16 * v, 64 );
+      if ( NV > 1 ) makeViewFilter( vps + 16 * v, args.filter[v] );
     }
+    args.useFilter = ( NV > 1 && ctx->optFilter ) ? 1 : 0;
     // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
     // issue-bound and the view-sequential packed kernel (cull_views.cuh) is the faster exact form
     const bool peers     = args.nPeers > 0;
@@ -2073,6 +2141,7 @@ extern "C"
       case DPCU_CULL_OPT_PROFILE:      ctx->optProfile = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FUSE_LEAF:    ctx->optFuseLeaf = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FUSE_LIST:    ctx->optFuseList = value ? 1 : 0; break;
+      case DPCU_CULL_OPT_FILTER:       ctx->optFilter = value ? 1 : 0; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -2091,6 +2160,7 @@ extern "C"
       case DPCU_CULL_OPT_FUSE_LEAF:    *value = ctx->optFuseLeaf; break;
       case DPCU_CULL_OPT_FUSE_LIST:    *value = ctx->optFuseList; break;
       case DPCU_CULL_OPT_LAST_KERNEL:  *value = ctx->lastKernel; break;
+      case DPCU_CULL_OPT_FILTER:       *value = ctx->optFilter; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -2111,6 +2181,24 @@ extern "C"
     *totalMs = sum;
     *launches = ctx->profUsed / 2;
     ctx->profUsed = 0;
+    return DPCU_OK;
+  }
+
+  int dpcuDebugKernelArgLayout( int nViews, size_t *onePairOffset, size_t *viewProjectionOffset, size_t *filterOffset, size_t *totalBytes )
+  {
+    DPCU_REQUIRE( nViews >= 1 && nViews <= DPCU_MAX_VIEWS, "nViews must be 1..DPCU_MAX_VIEWS" );
+    size_t one = 0, vp = 0, filter = 0, total = 0;
+    switch ( nViews )
+    {
+#define DPCU_LAYOUT( NV ) case NV: one = offsetof( dpcu::CullArgs<NV>, onePair ); vp = offsetof( dpcu::CullArgs<NV>, vp ); \
+                                   filter = offsetof( dpcu::CullArgs<NV>, filter ); total = sizeof( dpcu::CullArgs<NV> ); break;
+      DPCU_LAYOUT( 1 ) DPCU_LAYOUT( 2 ) DPCU_LAYOUT( 3 ) DPCU_LAYOUT( 4 ) DPCU_LAYOUT( 5 ) DPCU_LAYOUT( 6 ) DPCU_LAYOUT( 7 ) DPCU_LAYOUT( 8 )
+#undef DPCU_LAYOUT
+    }
+    if ( onePairOffset ) *onePairOffset = one;
+    if ( viewProjectionOffset ) *viewProjectionOffset = vp;
+    if ( filterOffset ) *filterOffset = filter;
+    if ( totalBytes ) *totalBytes = total;
     return DPCU_OK;
   }
 

@@ -38,37 +38,82 @@ def _kernels(funcs, stem):
     return {k: v for k, v in funcs.items() if stem in k}
 
 
+PARAM_BASE = 0x380            # kernel parameters start here in constant bank 0 on sm_100
+
+
+def _arg_layout(nv):
+    import ctypes as C
+    L = C.CDLL(LIB)
+    one, vp, flt, total = (C.c_size_t() for _ in range(4))
+    L.dpcuDebugKernelArgLayout.argtypes = [C.c_int] + [C.POINTER(C.c_size_t)] * 4
+    assert L.dpcuDebugKernelArgLayout(nv, C.byref(one), C.byref(vp), C.byref(flt), C.byref(total)) == 0
+    return {"one": PARAM_BASE + one.value, "vp": PARAM_BASE + vp.value, "filter": PARAM_BASE + flt.value,
+            "end": PARAM_BASE + total.value}
+
+
+_LOAD = re.compile(r"(?:@!?U?P\d+\s+)?(LDCU|LDC)(?:\.(\d+))?\s+(U?R\d+),\s*c\[0x0\]\[(?:(U?R\d+)\+)?(0x[0-9a-f]+)\]")
+_DEST = re.compile(r"(?:@!?U?P\d+\s+)?\S+\s+(U?R\d+)\b")
+
+
+def _constant_source(body, pos, reg):
+    """Constant-bank offset the nearest preceding definition of `reg` loaded it from (None: not a constant load;
+    a wide load covers the following registers as well).  Linear scan - good enough for straight-line loop bodies."""
+    kind, num = ("UR", int(reg[2:])) if reg.startswith("UR") else ("R", int(reg[1:]))
+    for back in range(pos - 1, -1, -1):
+        m = _LOAD.match(body[back])
+        if m:
+            width = int(m.group(2) or 32) // 32
+            dk, dn = ("UR", int(m.group(3)[2:])) if m.group(3).startswith("UR") else ("R", int(m.group(3)[1:]))
+            if dk == kind and dn <= num < dn + width:
+                return int(m.group(5), 16)
+            continue
+        d = _DEST.match(body[back])
+        if d and d.group(1) == reg:
+            return None
+    return None
+
+
 def test_exact_kernels_have_no_contracted_multiply_add(sass):
+    """The reference arithmetic must round every product and every sum separately.  In the kernels that carry
+    it, a fused multiply-add may only be (a) the packed add-of-a-product idiom: FFMA2 (packed product) * one +
+    (packed product) with `one` = CullArgs::onePair, or (b) arithmetic of the multi-view filter (cull_filter.cuh),
+    recognisable by an operand loaded from the filter constants; in particular nothing that multiplies by a
+    view-projection entry may be fused."""
     exact = {k: v for k, v in sass.items()
-             if any(s in k for s in ("cullDirectKernel", "cullViewsKernel", "cullStagedKernel", "treeLevelKernel",
+             if any(s in k for s in ("cullDirectKernel", "cullViewsKernel", "cullStagedKernel", "cullLinesKernel",
+                                     "cullFusedLeafKernel", "treeLevelKernel", "treeLevelWideKernel",
                                      "boundingBoxKernel")) and "_fma" not in k}
-    assert len(exact) >= 8 * 3 + 2
+    assert len(exact) >= 8 * 6 + 3
+    checked_filter = 0
     for name, body in exact.items():
-        scalar = [i for i in body if re.match(r"(@!?U?P\d+\s+)?FFMA\b", i)]
-        assert not scalar, "%s contains scalar FFMA: %s" % (name, scalar[:3])
-        # every FFMA2 must be addProd: (packed product) * one + (packed product).  `one` arrives as a kernel
-        # argument: the uniform register used as multiplier must have been loaded, by the nearest preceding
-        # definition in program order, from ONE fixed constant-bank address per kernel (CullArgs::onePair),
-        # never from the indexed view-projection rows, and the multiplicand is never a scalar broadcast
-        sources = set()
+        m = re.search(r"Kernel(?:I|_fmaI)Li(\d)E", name)
+        layout = _arg_layout(int(m.group(1))) if m else None
         for pos, i in enumerate(body):
-            if not re.match(r"(@!?U?P\d+\s+)?FFMA2\b", i):
+            mm = re.match(r"(?:@!?U?P\d+\s+)?(FFMA2?)\b(.*)", i)
+            if not mm:
                 continue
-            ops = [o.strip() for o in i.split(None, 1)[1].rstrip(" ;").split(",")]
-            assert len(ops) == 4, i
-            assert ops[1].endswith(".F32x2.HI_LO") and ops[1].startswith("R"), "%s: %s" % (name, i)
+            packed = mm.group(1) == "FFMA2"
+            ops = [o.strip() for o in i.split(None, 2 if i.startswith("@") else 1)[-1].rstrip(" ;").split(",")]
+            assert layout is not None, "%s contains %s" % (name, i)
+            regs = [re.match(r"-?\|?(U?R\d+)", o).group(1) for o in ops[1:] if re.match(r"-?\|?(U?R\d+)", o)]
+            sources = [_constant_source(body, pos, r) for r in regs]
+            if any(src is not None and layout["filter"] <= src < layout["end"] for src in sources):
+                checked_filter += 1                       # (b) the filter's own arithmetic
+                continue
+            # (a) addProd
+            assert packed, "%s: scalar fused multiply-add outside the filter: %s" % (name, i)
+            assert len(ops) == 4 and ops[1].endswith(".F32x2.HI_LO") and ops[1].startswith("R"), "%s: %s" % (name, i)
             assert ops[2].startswith("UR"), "%s: %s" % (name, i)
-            ur = ops[2].split(".")[0]
-            for back in range(pos - 1, -1, -1):
-                m = re.match(r"(@!?U?P\d+\s+)?(LDCU(?:\.\d+)?|UMOV)\s+%s,\s*(\S+)\s*;" % ur, body[back])
-                if m:
-                    if m.group(2) != "UMOV":            # (a UMOV copies a half loaded elsewhere)
-                        sources.add(m.group(3))
-                    break
-            else:
-                raise AssertionError("%s: no definition of %s before %s" % (name, ur, i))
-        assert len(sources) <= 1, "%s: FFMA2 multipliers come from %s" % (name, sources)
-        assert all("UR" not in a for a in sources), "%s: FFMA2 multiplier loaded from an indexed address %s" % (name, sources)
+            src = _constant_source(body, pos, ops[2].split(".")[0])
+            if src is None:                               # a UMOV of a half loaded elsewhere: follow it once
+                for back in range(pos - 1, -1, -1):
+                    u = re.match(r"(?:@!?U?P\d+\s+)?UMOV\s+%s,\s*(UR\d+)" % ops[2].split(".")[0], body[back])
+                    if u:
+                        src = _constant_source(body, back, u.group(1))
+                        break
+            assert src is not None and layout["one"] <= src < layout["one"] + 8, \
+                "%s: FFMA2 multiplier is not CullArgs::onePair (%s): %s" % (name, src, i)
+    assert checked_filter > 0
 
 
 def test_fma_variant_is_really_fused(sass):
