@@ -214,9 +214,9 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 
 /* Tuning / reporting knobs (never change results unless stated). */
 #define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
-#define DPCU_KERNEL_AUTO    0           /* the measured winner: line-granular (list built in-kernel) for large */
-                                        /* groups with 1 or >= 4 views, peer bitsets or a host mirror; else    */
-                                        /* direct (1 view) / view-sequential packed (>= 2 views)               */
+#define DPCU_KERNEL_AUTO    0           /* the measured winner: line-granular (list built in-kernel) for groups */
+                                        /* of >= 4.8 M objects and whenever peer bitsets are set; else direct   */
+                                        /* (1 view) / view-sequential packed (>= 2 views)                       */
 #define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */
 #define DPCU_KERNEL_STAGED  2           /* persistent CTAs, TMA bulk + cp.async staging in shared memory     */
 #define DPCU_KERNEL_VIEWS   3           /* views one after the other, packed f32x2 arithmetic                */
@@ -235,7 +235,9 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* (single-pass look-back); 0 = segment counters + compaction kernel       */
 #define DPCU_CULL_OPT_FILTER        9   /* 1 (default) = multi-view culls decide provable (object, view) pairs from  */
                                         /* the OBB's centre and radius and run the reference arithmetic only on the  */
-                                        /* rest (same bits, proof in cull_filter.cuh); 0 = reference arithmetic for all */
+                                        /* rest (same bits, proof in cull_filter.cuh); 0 = reference arithmetic for all; */
+                                        /* 2 / 3 = DIAGNOSTICS ONLY: margin shrunk to 1/8 (the error bound itself) / 0,  */
+                                        /* used by the tests to measure the slack of the proof                           */
 #define DPCU_CULL_OPT_LAST_KERNEL   8   /* read-only: DPCU_KERNEL_* form the last cull ran                          */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);

@@ -1278,7 +1278,7 @@ namespace dpcu
     float f = static_cast<float>( x );
     return ( static_cast<double>( f ) < x ) ? nextafterf( f, INFINITY ) : f;
   }
-  static void makeViewFilter( float const *vp, ViewFilter &f )
+  static void makeViewFilter( float const *vp, ViewFilter &f, double marginScale )
   {
     double P[4][4];
     for ( int r = 0; r < 4; ++r ) for ( int c = 0; c < 4; ++c ) P[r][c] = vp[4 * r + c];
@@ -1299,7 +1299,7 @@ namespace dpcu
                               roundUp( sqrt( n[1][0] * n[1][0] + n[1][1] * n[1][1] + n[1][2] * n[1][2] ) * inflate ) );
     }
     double q[4];
-    for ( int r = 0; r < 4; ++r ) q[r] = ( fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] ) ) / 131072.0;
+    for ( int r = 0; r < 4; ++r ) q[r] = marginScale * ( fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] ) ) / 131072.0;
     f.q = make_float4( roundUp( q[0] ), roundUp( q[1] ), roundUp( q[2] ), roundUp( q[3] ) );
   }
 
@@ -1330,7 +1330,9 @@ namespace dpcu
       if ( uint32_t( r->nPeers ) > args.nPeers ) args.nPeers = uint32_t( r->nPeers );
       args.peerWordOffset = uint32_t( r->peerWordOffset );
       memcpy( args.vp[v], vps + 16 * v, 64 );
-      if ( NV > 1 ) makeViewFilter( vps + 16 * v, args.filter[v] );
+      // DPCU_CULL_OPT_FILTER 2 / 3 shrink the margin to 1/8 (the bound of the error analysis itself) / to zero:
+      // diagnostics that measure the slack of the proof, never for production
+      if ( NV > 1 ) makeViewFilter( vps + 16 * v, args.filter[v], ctx->optFilter == 2 ? 0.125 : ctx->optFilter == 3 ? 0.0 : 1.0 );
     }
     args.useFilter = ( NV > 1 && ctx->optFilter ) ? 1 : 0;
     // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
@@ -1340,13 +1342,14 @@ namespace dpcu
     for ( int v = 0; v < NV; ++v ) mirrors = mirrors || results[v]->dBits != nullptr;
     // Whole 128-byte lines are what NVLink peers and PCIe host mirrors want to see, and the line-granular form
     // builds the changed list in the same pass (no compaction kernel): measured at 64 Mi objects, step time with
-    // an ordered changed list, lines vs the alternative - 1 view 1.009 vs 1.021 ms (direct + compaction), 6 views
-    // 2.631 vs 2.643 ms (views + compaction), 2 views 1.16 vs 1.14 ms.  A warp per 1024 objects needs a few
-    // million objects to fill the machine; below that AUTO stays with one thread per object (and serves a host
-    // mirror by a copy queued behind the kernel: 86 us per step in-kernel vs 79 us copied at 1 Mi objects).
+    // an ordered changed list, lines vs the alternative - 1 view 1.009 vs 1.021 ms (direct + compaction), 2 views
+    // 1.093 vs 1.149 ms, 3 views 1.285 vs 1.33 ms, 6 views 2.10 vs 2.26 ms (views + compaction).  A warp per 1024
+    // objects needs a few million objects to fill the machine; below that AUTO stays with one thread per object
+    // (and serves a host mirror by a copy queued behind the kernel: 86 us per step in-kernel vs 79 us copied at
+    // 1 Mi objects).
     const bool bigEnough = ctx->n >= size_t( ctx->smCount ) * 32u * 1024u;
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
-                        && ( mirrors || ( ctx->optChanged && ctx->optFuseList && ( NV == 1 || NV >= 4 ) ) );
+                        && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
     const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || autoLines );
     *mirrorsWritten = useLines && !leaf;
     const bool fuseList = useLines && !leaf && ctx->optChanged && ctx->optFuseList;
@@ -2141,7 +2144,7 @@ extern "C"
       case DPCU_CULL_OPT_PROFILE:      ctx->optProfile = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FUSE_LEAF:    ctx->optFuseLeaf = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FUSE_LIST:    ctx->optFuseList = value ? 1 : 0; break;
-      case DPCU_CULL_OPT_FILTER:       ctx->optFilter = value ? 1 : 0; break;
+      case DPCU_CULL_OPT_FILTER:       DPCU_REQUIRE( value >= 0 && value <= 3, "filter must be 0..3" ); ctx->optFilter = value; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;

@@ -146,6 +146,17 @@ def test_c4_sixty_four_million_six_views(capi, port):
             union = np.bitwise_or.reduce(np.stack(new))
             assert _popcount(union) / n > 0.95
         old = new
+    # the multi-view filter decides only what it can prove: reference arithmetic for every pair (filter off) and
+    # the filter with 1/8 of its margin (the rounding-error bound of the proof itself) give the same words
+    for mode in (0, 2):
+        sc.ctx.set_option(capi.OPT_FILTER, mode)
+        again = [sc.ctx.result_create() for _ in range(6)]
+        sc.ctx.run(again, vps)
+        for v in range(6):
+            assert np.array_equal(again[v].bits(), old[v]), (mode, v)
+        for r in again:
+            r.close()
+    sc.ctx.set_option(capi.OPT_FILTER, 1)
     # one six-view pass == six single-view passes (new results: compare words only)
     single = sc.ctx.result_create()
     for v in range(6):
