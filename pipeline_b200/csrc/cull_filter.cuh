@@ -23,8 +23,10 @@
 //   E: the reference forms every clip coordinate from at most 8 rounded operations on terms whose
 //   absolute values sum to at most  S = sum_r (|p_r| + |a_r| + |b_r| + |c_r|) * sum_c |P[r][c]|,
 //   so its error is below 8u S / (1 - 8u), u = 2^-24; the filter's own centre / plane / support
-//   arithmetic adds less than another 8u S.  The margin used is 2^-17 S (8x that sum); supports
-//   are bounded by Cauchy-Schwarz with radius and plane norms rounded up.  A decision is taken
+//   arithmetic adds less than another 8u S.  The margin used is 2^-17 S' with
+//   S' = max_r (|p_r| + |a_r| + |b_r| + |c_r|) * sum_r sum_c |P[r][c]| >= S  (at least 8x the sum of the two
+//   errors; one multiply per object and view); supports are bounded by Cauchy-Schwarz with radius and plane
+//   norms rounded up.  A decision is taken
 //   only when a comparison is TRUE, so NaN never decides, and only when S < 2^96 (nothing
 //   overflowed).  Everything else - and every warp that holds a non-affine object or a
 //   non-finite view-projection - takes the reference arithmetic of cull_views.cuh.
@@ -44,7 +46,7 @@ namespace dpcu
   {
     float2 nx[3], ny[3], nz[3], nw[3];   // plane functions per axis (x, y, z): .x = N plane (col_a + col_w), .y = P plane (col_w - col_a)
     float2 rho[3];                       // |plane.xyz|_2, rounded up
-    float4 q;                            // 2^-17 * sum_c |P[r][c]| per row r: margin = q . (aw, 1)
+    float4 q;                            // q.x = 2^-17 * sum_r sum_c |P[r][c]|: margin = q.x * max(aw, 1) >= 2^-17 S
   };
 
   __device__ __forceinline__ f32x2 fma2( f32x2 a, f32x2 b, f32x2 c )
@@ -70,7 +72,7 @@ namespace dpcu
   {
     float cx, cy, cz;      // centre
     float r;               // >= half diagonal
-    float awx, awy, awz;   // |p| + |a| + |b| + |c| per component
+    float aw;              // max over components of |p| + |a| + |b| + |c|, and 1 (the w component of p)
   };
 
   __device__ __forceinline__ ObbSphere makeSphere( Obb const &o )
@@ -84,9 +86,11 @@ namespace dpcu
     const float lc = sqrtApprox( o.az.x * o.az.x + o.az.y * o.az.y + o.az.z * o.az.z );
     // 0.5 * (1 + 2^-20): rounded up past the sqrt / add errors; 2^-60: components whose squares underflowed
     s.r   = ( ( la + lb ) + lc ) * 0.50000048f + 8.7e-19f;
-    s.awx = ( fabsf( o.pt.x ) + fabsf( o.ax.x ) ) + ( fabsf( o.ay.x ) + fabsf( o.az.x ) );
-    s.awy = ( fabsf( o.pt.y ) + fabsf( o.ax.y ) ) + ( fabsf( o.ay.y ) + fabsf( o.az.y ) );
-    s.awz = ( fabsf( o.pt.z ) + fabsf( o.ax.z ) ) + ( fabsf( o.ay.z ) + fabsf( o.az.z ) );
+    const float awx = ( fabsf( o.pt.x ) + fabsf( o.ax.x ) ) + ( fabsf( o.ay.x ) + fabsf( o.az.x ) );
+    const float awy = ( fabsf( o.pt.y ) + fabsf( o.ax.y ) ) + ( fabsf( o.ay.y ) + fabsf( o.az.y ) );
+    const float awz = ( fabsf( o.pt.z ) + fabsf( o.ax.z ) ) + ( fabsf( o.ay.z ) + fabsf( o.az.z ) );
+    // S = sum_r aw_r * rowsum_r <= max_r aw_r * sum_r rowsum_r; a NaN component must not get lost in fmaxf
+    s.aw = fmaxf( fmaxf( awx, awy ), fmaxf( awz, 1.0f ) ) + 0.0f * ( ( awx + awy ) + awz );
     return s;
   }
 
@@ -94,7 +98,7 @@ namespace dpcu
   __device__ __forceinline__ void classify( ObbSphere const &s, ViewFilter const &f, bool &visible, bool &invisible )
   {
     const f32x2 cx = pack2( s.cx, s.cx ), cy = pack2( s.cy, s.cy ), cz = pack2( s.cz, s.cz ), rr = pack2( s.r, s.r );
-    const float m = fmaf( s.awx, f.q.x, fmaf( s.awy, f.q.y, fmaf( s.awz, f.q.z, f.q.w ) ) );
+    const float m = s.aw * f.q.x;
     const float nm = -m;
     const bool sane = m < 6.0e23f;                         // S < 2^96 (q carries the 2^-17): nothing overflowed; false for NaN
     float fmin = 3.0e38f, hNmin = 3.0e38f;

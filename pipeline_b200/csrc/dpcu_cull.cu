@@ -1300,7 +1300,7 @@ namespace dpcu
     }
     double q[4];
     for ( int r = 0; r < 4; ++r ) q[r] = marginScale * ( fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] ) ) / 131072.0;
-    f.q = make_float4( roundUp( q[0] ), roundUp( q[1] ), roundUp( q[2] ), roundUp( q[3] ) );
+    f.q = make_float4( roundUp( ( q[0] + q[1] ) + ( q[2] + q[3] ) ), 0.0f, 0.0f, 0.0f );
   }
 
   template <int NV>
