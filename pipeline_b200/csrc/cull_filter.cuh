@@ -145,7 +145,11 @@ namespace dpcu
     scratch.obb[0][lane] = make_float4( obb.pt.x, obb.pt.y, obb.pt.z, obb.ax.x );
     scratch.obb[1][lane] = make_float4( obb.ax.y, obb.ax.z, obb.ay.x, obb.ay.y );
     scratch.obb[2][lane] = make_float4( obb.ay.z, obb.az.x, obb.az.y, obb.az.z );
-#pragma unroll
+#ifndef DPCU_FILTER_UNROLL
+#define DPCU_FILTER_UNROLL 8
+#endif
+    constexpr int kUnroll = DPCU_FILTER_UNROLL;
+#pragma unroll kUnroll
     for ( int v = 0; v < NV; ++v )
     {
       bool vis, inv;

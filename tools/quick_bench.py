@@ -35,7 +35,7 @@ def main():
     ctx.set_option(capi.OPT_FMA, a.fma)
     ctx.set_option(capi.OPT_CHANGED_LIST, a.changed)
     res = [ctx.result_create() for _ in range(a.views)]
-    cams = scenes.cube_map_cameras() if a.views > 1 else None
+    cams = np.concatenate([scenes.cube_map_cameras(), scenes.cube_map_cameras((50.0, 20.0, -30.0))]) if a.views > 1 else None
     s = capi.Stream()
     e0, e1 = capi.Event(), capi.Event()
 
