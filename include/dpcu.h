@@ -238,6 +238,8 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* rest (same bits, proof in cull_filter.cuh); 0 = reference arithmetic for all; */
                                         /* 2 / 3 = DIAGNOSTICS ONLY: margin shrunk to 1/8 (the error bound itself) / 0,  */
                                         /* used by the tests to measure the slack of the proof                           */
+#define DPCU_CULL_OPT_LINE_WORDS   10   /* line-granular kernel: bitset words per warp; 0 (default) = 32 (a 128-byte */
+                                        /* line); 8 / 16 = shorter lines (more warps on small groups; experiment)    */
 #define DPCU_CULL_OPT_LAST_KERNEL   8   /* read-only: DPCU_KERNEL_* form the last cull ran                          */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);

@@ -292,24 +292,4 @@ namespace dpcu
     return myWord;
   }
 
-  // The same, software-pipelined by one view: the products of view v+1 are issued next to the
-  // compares of view v.  Costs ~30 more registers; measured slower than cullViews on B200
-  // (occupancy matters more than the interleave), kept for experiments.
-  template <int NV, bool kAffine>
-  __device__ __forceinline__ uint32_t cullViewsPipelined( ObbPairs const &ob, float4 const ( *vp )[4], f32x2 one, bool live, uint32_t lane )
-  {
-    uint32_t myWord = 0;
-    ClipVectors cur = clipVectors<kAffine>( ob, loadViewPairs( vp[0] ), one );
-#pragma unroll 1
-    for ( int v = 0; v < NV - 1; ++v )
-    {
-      const ClipVectors next = clipVectors<kAffine>( ob, loadViewPairs( vp[v + 1] ), one );
-      const uint32_t b = __ballot_sync( 0xffffffffu, cornersVisible<true>( cur ) & live );
-      if ( lane == uint32_t( v ) ) myWord = b;
-      cur = next;
-    }
-    const uint32_t b = __ballot_sync( 0xffffffffu, cornersVisible<true>( cur ) & live );
-    if ( lane == uint32_t( NV - 1 ) ) myWord = b;
-    return myWord;
-  }
 }

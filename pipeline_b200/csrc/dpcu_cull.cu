@@ -73,6 +73,7 @@ namespace dpcu
     uint32_t     *chunkCounter;   // staged kernel: next unclaimed chunk of kChunkTiles tiles
     int           vpFinite;  // every view-projection entry is finite (enables the affine shortcut of cull_views.cuh)
     unsigned long long onePair;   // (1.0f, 1.0f): runtime multiplier of cull_views.cuh::addProd
+    uint32_t      lineWords; // line-granular kernel: bitset words per warp (32 = one 128-byte line; 8 for mid-size groups)
     int           useFilter; // cull_filter.cuh: decide provable (object, view) pairs from centre and radius
     ViewOut       out[NV];
     float4        vp[NV][4];
@@ -547,13 +548,14 @@ namespace dpcu
   template <int NV>
   __device__ __forceinline__ void resolveLine( CullArgs<NV> const &a, uint32_t line, uint32_t nLines, uint32_t nWords, uint32_t lane )
   {
-    const uint32_t myWord = ( line << 5 ) + lane;
+    const uint32_t myWord = line * a.lineWords + lane;
+    const bool     mine   = lane < a.lineWords && myWord < nWords;
     __syncwarp();                                            // the warp's chg stores of that line are visible to all its lanes
 #pragma unroll 1
     for ( int v = 0; v < NV; ++v )
     {
       ViewOut const &o = a.out[v];
-      uint32_t c = myWord < nWords ? __ldcg( o.chg + myWord ) : 0u;
+      uint32_t c = mine ? __ldcg( o.chg + myWord ) : 0u;
       const uint32_t flips = __popc( c );
       uint32_t incl = flips;                                 // inclusive scan of the per-word counts across the line
 #pragma unroll
@@ -610,7 +612,8 @@ namespace dpcu
   cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane   = threadIdx.x & 31u;
-    const uint32_t nWords = ( a.n + 31u ) >> 5, nLines = ( nWords + 31u ) >> 5;
+    const uint32_t W = a.lineWords;
+    const uint32_t nWords = ( a.n + 31u ) >> 5, nLines = ( nWords + W - 1u ) / W;
     const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
     uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 );
     uint32_t pending = kNoLine;
@@ -627,8 +630,8 @@ namespace dpcu
         line = __shfl_sync( 0xffffffffu, claimed, 0 );
       }
       if ( line >= nLines ) break;
-      const uint32_t word0 = line << 5, myWord = word0 + lane;
-      const bool     wordLive = myWord < nWords;
+      const uint32_t word0 = line * W, myWord = word0 + lane;
+      const bool     wordLive = lane < W && myWord < nWords;
       uint32_t old[NV], acc[NV];
 #pragma unroll
       for ( int v = 0; v < NV; ++v )
@@ -636,12 +639,13 @@ namespace dpcu
         old[v] = wordLive ? a.out[v].bits[myWord] : 0u;
         acc[v] = 0u;
       }
-      const uint32_t steps = min( 32u, nWords - word0 );
+      const uint32_t steps = min( W, nWords - word0 );
       // With several views this kernel runs at 24-32 warps per SM and (since the filter) waits on memory more than
       // on the issue slots: the transform index two steps ahead is fetched now, the one fetched a step ago turns
       // into an L2 prefetch of the next step's matrices and extents (same scheme as cullViewsKernel).  Measured at
       // 64 Mi objects: 2 views 1.094 -> 1.054 ms, 4 views 1.559 -> 1.528 ms; with 5+ views the two extra registers
-      // spill (6 views 2.074 -> 2.159 ms), so those instantiations go without.
+      // spill (6 views 2.074 -> 2.159 ms), so those instantiations go without (prefetching only the object lines,
+      // which needs no register, changed nothing: 2.062 ms).
       constexpr bool kPrefetch = NV >= 2 && NV <= 4;
       uint32_t idxNext = 0;
       if ( kPrefetch )
@@ -1214,7 +1218,7 @@ struct dpcuCull
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1, optLineWords = 0;
   int          lastKernel = 0;           // DPCU_KERNEL_* of the last cull launched (DPCU_CULL_OPT_LAST_KERNEL)
   uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
   dpcuTree    *leafTree = nullptr;       // cached answer of the leaf-binding check of dpcuCullRunWithTree
@@ -1275,7 +1279,7 @@ namespace dpcu
       if ( r->nPeers == 0 ) { /* local only */ }
     }
     if ( ctx->optChanged ) DPCU_TRY( r->changed.reserve( ( n ? n : 1 ) * 4, false, stream ) );
-    size_t nLines = divUp( divUp( n, 32 ), 32 );
+    size_t nLines = divUp( divUp( n, 32 ), 8 );          // look-back entries for the finest line size
     if ( ctx->optChanged && nLines > r->lookCap )
     {
       DPCU_TRY( r->look.reserve( ( nLines + nLines / 2 + 64 ) * 8, false, stream ) );
@@ -1371,9 +1375,13 @@ namespace dpcu
     // objects needs a few million objects to fill the machine; below that AUTO stays with one thread per object
     // (and serves a host mirror by a copy queued behind the kernel: 86 us per step in-kernel vs 79 us copied at
     // 1 Mi objects).
+    // (The same kernel with 8 or 16 bitset words per warp - DPCU_CULL_OPT_LINE_WORDS - fills the machine on
+    // mid-size groups but does not beat direct + compaction there: 1 / 2 / 4 Mi objects 57 / 81 / 114 us vs
+    // 48 / 70 / 108 us per step.)
     const bool bigEnough = ctx->n >= size_t( ctx->smCount ) * 32u * 1024u;
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
+    args.lineWords = ctx->optLineWords ? uint32_t( ctx->optLineWords ) : 32u;
     const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || autoLines );
     *mirrorsWritten = useLines && !leaf;
     const bool fuseList = useLines && !leaf && ctx->optChanged && ctx->optFuseList;
@@ -1458,7 +1466,7 @@ namespace dpcu
     }
     else if ( useLines )
     {
-      const uint32_t nLines = uint32_t( divUp( divUp( ctx->n, 32 ), 32 ) );
+      const uint32_t nLines = uint32_t( divUp( divUp( ctx->n, 32 ), args.lineWords ) );
       const uint32_t ctasForLines = uint32_t( divUp( nLines, kCullThreads / 32 ) );
       if ( uint32_t( grid ) > ctasForLines ) grid = int( ctasForLines );
       if ( fuseList ) cullLinesKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
@@ -2169,6 +2177,8 @@ extern "C"
       case DPCU_CULL_OPT_FUSE_LEAF:    ctx->optFuseLeaf = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FUSE_LIST:    ctx->optFuseList = value ? 1 : 0; break;
       case DPCU_CULL_OPT_FILTER:       DPCU_REQUIRE( value >= 0 && value <= 3, "filter must be 0..3" ); ctx->optFilter = value; break;
+      case DPCU_CULL_OPT_LINE_WORDS:   DPCU_REQUIRE( value == 0 || value == 8 || value == 16 || value == 32, "line words must be 0 (auto), 8, 16 or 32" );
+                                       ctx->optLineWords = value; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -2188,6 +2198,7 @@ extern "C"
       case DPCU_CULL_OPT_FUSE_LIST:    *value = ctx->optFuseList; break;
       case DPCU_CULL_OPT_LAST_KERNEL:  *value = ctx->lastKernel; break;
       case DPCU_CULL_OPT_FILTER:       *value = ctx->optFilter; break;
+      case DPCU_CULL_OPT_LINE_WORDS:   *value = ctx->optLineWords; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
     return DPCU_OK;

@@ -207,13 +207,15 @@ def test_multi_view_equals_single_views(capi, port):
 # ------------------------------------------------------------------ both exact kernel forms, 1..8 views
 # every exact form of K2: DPCU_KERNEL_* plus, for the line-granular kernel, how the changed list is built
 # (inside the kernel by single-pass look-back, the default, or by segment counters + the compaction kernel)
-KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4}
+KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4, "lines_w8": 4}
 
 
 def _select_kernel(capi, ctx, kernel):
     ctx.set_option(capi.OPT_KERNEL, dict(KERNELS, auto=0)[kernel])
     if kernel.endswith("_compact"):
         ctx.set_option(capi.OPT_FUSE_LIST, 0)
+    if kernel.endswith("_w8"):
+        ctx.set_option(capi.OPT_LINE_WORDS, 8)              # a warp per 256 objects (the mid-size form)
 
 
 
@@ -709,7 +711,7 @@ class _Mirror:
             b.close()
 
 
-@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact"])
+@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact", "lines_w8"])
 @pytest.mark.parametrize("nv", [1, 3])
 def test_host_mirror_matches_port(capi, port, kernel, nv):
     """dpcuCullResultSetHostMirror: after run + synchronize the pinned buffers hold exactly what
