@@ -606,9 +606,12 @@ namespace dpcu
     if ( sLastLines && threadIdx.x == 0 ) done[0] = done[1] = 0u;      // ticket and line counter: ready for the next cull
   }
 
-  // measured at 64 Mi objects: 2 views 1.55 / 1.23 / 1.16 ms and 6 views 2.82 / 2.61 / 2.64 ms at 2 / 3 / 4 CTAs per SM
+  // measured at 64 Mi objects before the filter: 2 views 1.55 / 1.23 / 1.16 ms and 6 views 2.82 / 2.61 / 2.64 ms at
+  // 2 / 3 / 4 CTAs per SM;
+  // with the filter (fewer issue slots, more waiting on memory) 4 CTAs per SM win for every multi-view count:
+  // 6 views 2.068 ms at 3 CTAs (80 registers) -> 1.937 ms at 4 (64 registers, ~70 bytes of spills)
   template <int NV, bool kFuseList>
-  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : ( NV <= 3 ? 4 : 3 ) )
+  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : 4 )
   cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane   = threadIdx.x & 31u;
