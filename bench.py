@@ -249,6 +249,49 @@ def cpu_baseline_single_core(workload, seed):
                       "first cull incl. OBB build %.1f M objects/s; setup %.1f s" % (n, workload, seed, n / first / 1e6, setup_s)}
 
 
+def cpu_tree_baseline(seed):
+    """C3 only: dp::transform::Tree::compute on the host (SURVEY.md 8d), every node dirty, on a 1/16-scale tree
+    (256 / 4096 / 65536 / 1048576 nodes - building the full 17.9 M-node tree through addTransform takes minutes)."""
+    from oracle import loader
+    from pipeline_b200 import scenes
+    levels = (256, 4096, 65536, 1048576)
+    n_nodes = 1 + sum(levels)
+    if loader.Reference.available():
+        tree = loader.Reference().tree()
+        parents = np.zeros(levels[0], np.uint32)
+        first = 1
+        for k, n in enumerate(levels):
+            idx = tree.add_many(parents, scenes.random_objects(seed + 1, first, n)[3])
+            first += n
+            if k + 1 < len(levels):
+                parents = np.repeat(idx, levels[k + 1] // n)
+        secs = []
+        for it in range(6):
+            tree.update_locals(np.arange(1, n_nodes, dtype=np.uint32), scenes.random_objects(seed + 1, 1, n_nodes - 1)[3])
+            t0 = time.perf_counter()
+            tree.compute()
+            secs.append(time.perf_counter() - t0)
+        kind = "reference"
+    else:
+        port = loader.Port()
+        entries, offsets, n_nodes = scenes.hierarchy_topology(levels)
+        local = np.zeros((n_nodes, 4, 4), np.float32)
+        local[0] = np.eye(4, dtype=np.float32)
+        local[1:] = scenes.random_objects(seed + 1, 1, n_nodes - 1)[3]
+        world = np.zeros_like(local)
+        world[0] = local[0]
+        nw = (n_nodes + 31) // 32
+        secs = []
+        for it in range(6):
+            t0 = time.perf_counter()
+            port.tree_compute(local, world, entries, offsets, np.full(nw, 0xFFFFFFFF, np.uint32), np.zeros(nw, np.uint32))
+            secs.append(time.perf_counter() - t0)
+        kind = "port"
+    med = float(np.median(secs[1:]))
+    return {"transform_nodes_per_s": (n_nodes - 1) / med, "transform_kind": kind,
+            "transform_sample": "Tree::compute, %d nodes in 4 levels (1/16 of the C3 tree), all dirty, 1 core, median of 5" % (n_nodes - 1)}
+
+
 # ------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -612,6 +655,8 @@ def run_ours(args, rank, world, local_rank):
         line["also"] = also
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single_core(args.workload, seed)
+        if tree is not None:
+            line["cpu_baseline"].update(cpu_tree_baseline(seed))
     if rank == 0:
         print(json.dumps(line), flush=True)
     for r in results:
