@@ -1373,15 +1373,19 @@ namespace dpcu
     for ( int v = 0; v < NV; ++v ) mirrors = mirrors || results[v]->dBits != nullptr;
     // Whole 128-byte lines are what NVLink peers and PCIe host mirrors want to see, and the line-granular form
     // builds the changed list in the same pass (no compaction kernel): measured at 64 Mi objects, step time with
-    // an ordered changed list, lines vs the alternative - 1 view 1.009 vs 1.021 ms (direct + compaction), 2 views
-    // 1.093 vs 1.149 ms, 3 views 1.285 vs 1.33 ms, 6 views 2.10 vs 2.26 ms (views + compaction).  A warp per 1024
-    // objects needs a few million objects to fill the machine; below that AUTO stays with one thread per object
-    // (and serves a host mirror by a copy queued behind the kernel: 86 us per step in-kernel vs 79 us copied at
-    // 1 Mi objects).
+    // an ordered changed list, lines vs the alternative - 1 view 1.003 vs 1.021 ms (direct + compaction), 2 views
+    // 1.093 vs 1.149 ms, 3 views 1.285 vs 1.33 ms, 6 views 1.93 vs 2.26 ms (views + compaction).  A warp works
+    // through whole 1024-object lines, so the kernel wants several lines per resident warp: with 1 view it loses
+    // to direct + compaction below ~32 Mi objects (8 Mi: 0.192 vs 0.161 ms, 16 Mi: 0.298 vs 0.277 ms, 32 Mi: 0.530
+    // vs 0.535 ms per step) - AUTO asks for four lines per resident warp there; with several views (where the
+    // alternative is the views kernel) one line per resident warp is enough: 6 views, 8 Mi objects 0.280 vs 0.307 ms,
+    // 16 Mi 0.502 vs 0.588 ms.  Below that it stays with one thread per object and serves a host mirror by a copy
+    // queued behind the kernel.
     // (The same kernel with 8 or 16 bitset words per warp - DPCU_CULL_OPT_LINE_WORDS - fills the machine on
-    // mid-size groups but does not beat direct + compaction there: 1 / 2 / 4 Mi objects 57 / 81 / 114 us vs
+    // mid-size groups but does not beat direct + compaction there either: 1 / 2 / 4 Mi objects 57 / 81 / 114 us vs
     // 48 / 70 / 108 us per step.)
-    const bool bigEnough = ctx->n >= size_t( ctx->smCount ) * 32u * 1024u;
+    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 4u * 48u : 32u );
+    const bool bigEnough = divUp( divUp( ctx->n, 32 ), 32 ) >= wantedLines;
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
     args.lineWords = ctx->optLineWords ? uint32_t( ctx->optLineWords ) : 32u;
