@@ -97,6 +97,36 @@ def test_same_driver_two_backends_special_and_gather(dropin, golden):
 
 
 @pytest.mark.gpu
+def test_same_driver_two_backends_growing_group(dropin):
+    """The group grows past the capacity of the result's pinned host mirror several times (ResultCUDA::prepare
+    re-pins and re-registers it) and shrinks again; bitsets, changed lists and per-object visibility queries
+    stay identical to the reference backend."""
+    n = 40000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n)
+    a, b = RefEngine(dropin, 0), RefEngine(dropin, 1)
+    for e in (a, b):
+        e.set_matrices(mats.reshape(-1))
+    have = 0
+    frames = cases.frames(6)
+    for k, grow in enumerate((700, 1500, 9000, 28800)):
+        for e in (a, b):
+            e.add(lower4[have:have + grow], upper4[have:have + grow], tidx[have:have + grow])
+        have += grow
+        for vp in frames[k:k + 2]:
+            ab, ac = a.cull(vp)
+            bb, bc = b.cull(vp)
+            assert np.array_equal(ab, bb), (k, "bits")
+            assert np.array_equal(ac, bc), (k, "changed list")
+    for e in (a, b):
+        for gi in (0, 39999 - 1, 123, 20000):
+            e.remove(gi)
+    ab, ac = a.cull(frames[5])
+    bb, bc = b.cull(frames[5])
+    assert np.array_equal(ab, bb) and np.array_equal(ac, bc)
+    a.close(), b.close()
+
+
+@pytest.mark.gpu
 def test_dirty_matrix_protocol(dropin):
     """groupMatrixChanged -> only the flagged matrices are re-read (GroupBitSet.h:140-150)."""
     lower4, extent4, upper4, mats, tidx = cases.random_case(4096)
