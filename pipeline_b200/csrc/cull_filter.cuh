@@ -44,9 +44,12 @@ namespace dpcu
   // per view, computed on the host in double precision from the view-projection (see makeViewFilter)
   struct ViewFilter
   {
-    float2 nx[3], ny[3], nz[3], nw[3];   // plane functions per axis (x, y, z): .x = N plane (col_a + col_w), .y = P plane (col_w - col_a)
-    float2 rho[3];                       // |plane.xyz|_2, rounded up
-    float4 q;                            // q.x = 2^-17 * sum_r sum_c |P[r][c]|: margin = q.x * max(aw, 1) >= 2^-17 S
+    float4 rows[4];    // the filter's own copy of the view-projection rows: its fused multiply-adds must be
+                       // distinguishable (by constant-bank address) from the reference arithmetic, which never fuses
+    float rhoN[3];     // per clip axis a: |(col_a + col_w).xyz|_2 of the view-projection, rounded up (N plane: x + w)
+    float rhoP[3];     //                  |(col_w - col_a).xyz|_2, rounded up                        (P plane: w - x)
+    float q;           // 2^-17 * sum_r sum_c |P[r][c]|: margin = q * max(aw, 1) >= 2^-17 S
+    float pad;
   };
 
   __device__ __forceinline__ f32x2 fma2( f32x2 a, f32x2 b, f32x2 c )
@@ -54,10 +57,6 @@ namespace dpcu
     f32x2 r;
     asm( "fma.rn.f32x2 %0, %1, %2, %3;" : "=l"( r ) : "l"( a ), "l"( b ), "l"( c ) );
     return r;
-  }
-  __device__ __forceinline__ f32x2 asPair( float2 v )
-  {
-    return pack2( v.x, v.y );
   }
 
   __device__ __forceinline__ float sqrtApprox( float x )
@@ -94,31 +93,35 @@ namespace dpcu
     return s;
   }
 
-  // (V), (N), (P) above for one view: visible / invisible proven, or neither
+  // (V), (N), (P) above for one view: visible / invisible proven, or neither.  The plane functions at the centre
+  // come from its clip coordinates (A_x, A_y, A_z, W) = centre * P, one packed dot product per column pair:
+  // fN_a = W + A_a, fP_a = W - A_a, so (V) is  W - max_a |A_a| > m.
   __device__ __forceinline__ void classify( ObbSphere const &s, ViewFilter const &f, bool &visible, bool &invisible )
   {
-    const f32x2 cx = pack2( s.cx, s.cx ), cy = pack2( s.cy, s.cy ), cz = pack2( s.cz, s.cz ), rr = pack2( s.r, s.r );
-    const float m = s.aw * f.q.x;
-    const float nm = -m;
+    const ViewPairs P = loadViewPairs( f.rows );
+    const f32x2 cx = pack2( s.cx, s.cx ), cy = pack2( s.cy, s.cy ), cz = pack2( s.cz, s.cz );
+    const f32x2 lo = fma2( cx, P.p[0], fma2( cy, P.p[2], fma2( cz, P.p[4], P.p[6] ) ) );
+    const f32x2 hi = fma2( cx, P.p[1], fma2( cy, P.p[3], fma2( cz, P.p[5], P.p[7] ) ) );
+    float A[3], W;
+    unpack2( lo, A[0], A[1] );
+    unpack2( hi, A[2], W );
+    const float m = s.aw * f.q;
     const bool sane = m < 6.0e23f;                         // S < 2^96 (q carries the 2^-17): nothing overflowed; false for NaN
-    float fmin = 3.0e38f, hNmin = 3.0e38f;
-    bool invP = false;
+    // every value below is finite when m is (|value| <= S), so NaN cannot hide behind fminf / fmaxf
+    visible = sane & ( W - fmaxf( fabsf( A[0] ), fmaxf( fabsf( A[1] ), fabsf( A[2] ) ) ) > m );
+    const float kLow = -m - W, kHigh = m - W;              // f + support < -m  <=>  a-part < kLow ;  f - support > m  <=>  a-part > kHigh
+    float tN[3];
+    bool  inv = false;
 #pragma unroll
     for ( int a = 0; a < 3; ++a )
     {
-      const f32x2 F = fma2( cx, asPair( f.nx[a] ), fma2( cy, asPair( f.ny[a] ), fma2( cz, asPair( f.nz[a] ), asPair( f.nw[a] ) ) ) );
-      const f32x2 H = fma2( rr, asPair( f.rho[a] ), F );   // centre value + support
-      float fN, fP, hN, hP;
-      unpack2( F, fN, fP );
-      unpack2( H, hN, hP );
-      const float lN = fmaf( -s.r, f.rho[a].x, fN );       // centre value - support (N plane)
-      fmin  = fminf( fmin, fminf( fN, fP ) );              // NaN operands drop out of fminf: guarded by `sane` below
-      hNmin = fminf( hNmin, hN );
-      invP  = invP | ( ( hP < nm ) & ( lN > m ) );
+      tN[a] = fmaf( s.r, f.rhoN[a], A[a] );                                  // fN + support, without W
+      const float uP = fmaf( s.r, f.rhoP[a], -A[a] );                        // fP + support, without W
+      const float vN = fmaf( -s.r, f.rhoN[a], A[a] );                        // fN - support, without W
+      inv = inv | ( ( uP < kLow ) & ( vN > kHigh ) );                        // (P)
     }
-    // every value that entered a min is finite when m is (|value| <= S): NaN cannot hide behind fminf
-    visible   = sane & ( fmin > m );
-    invisible = sane & !visible & ( ( hNmin < nm ) | invP );
+    inv = inv | ( fminf( tN[0], fminf( tN[1], tN[2] ) ) < kLow );            // (N)
+    invisible = sane & !visible & inv;
   }
 
   // All NV views of the warp's 32 objects; every lane's object is affine and the view-projections are
@@ -133,8 +136,8 @@ namespace dpcu
   };
 
   template <int NV>
-  __device__ __forceinline__ uint32_t cullViewsFiltered( Obb const &obb, ViewFilter const ( &vf )[NV], f32x2 const *sP, FilterScratch<NV> &scratch,
-                                                         f32x2 one, bool live, uint32_t lane )
+  __device__ __forceinline__ uint32_t cullViewsFiltered( Obb const &obb, ViewFilter const ( &vf )[NV], f32x2 const *sP,
+                                                         FilterScratch<NV> &scratch, f32x2 one, bool live, uint32_t lane )
   {
     const ObbSphere s = makeSphere( obb );
     const uint32_t below = ( 1u << lane ) - 1u;

@@ -646,10 +646,9 @@ namespace dpcu
       // With several views this kernel runs at 24-32 warps per SM and (since the filter) waits on memory more than
       // on the issue slots: the transform index two steps ahead is fetched now, the one fetched a step ago turns
       // into an L2 prefetch of the next step's matrices and extents (same scheme as cullViewsKernel).  Measured at
-      // 64 Mi objects: 2 views 1.094 -> 1.054 ms, 4 views 1.559 -> 1.528 ms; with 5+ views the two extra registers
-      // spill (6 views 2.074 -> 2.159 ms), so those instantiations go without (prefetching only the object lines,
-      // which needs no register, changed nothing: 2.062 ms).
-      constexpr bool kPrefetch = NV >= 2 && NV <= 4;
+      // 64 Mi objects with the current filter: 2 views 1.174 -> 1.154 ms; 3 views 1.266 -> 1.276 ms, 4 views 1.441
+      // -> 1.499 ms and 6 views unchanged (the two extra registers spill there), so only NV == 2 keeps it.
+      constexpr bool kPrefetch = NV == 2;
       uint32_t idxNext = 0;
       if ( kPrefetch )
       {
@@ -1313,25 +1312,23 @@ namespace dpcu
   {
     double P[4][4];
     for ( int r = 0; r < 4; ++r ) for ( int c = 0; c < 4; ++c ) P[r][c] = vp[4 * r + c];
+    const double inflate = 1.0 + 1.0 / 1048576.0;
     for ( int a = 0; a < 3; ++a )
     {
-      double n[2][4];
-      for ( int r = 0; r < 4; ++r )
+      double nN[3], nP[3];
+      for ( int r = 0; r < 3; ++r )
       {
-        n[0][r] = P[r][a] + P[r][3];        // N plane: x + w
-        n[1][r] = P[r][3] - P[r][a];        // P plane: w - x
+        nN[r] = P[r][a] + P[r][3];          // N plane: x + w
+        nP[r] = P[r][3] - P[r][a];          // P plane: w - x
       }
-      f.nx[a] = make_float2( float( n[0][0] ), float( n[1][0] ) );
-      f.ny[a] = make_float2( float( n[0][1] ), float( n[1][1] ) );
-      f.nz[a] = make_float2( float( n[0][2] ), float( n[1][2] ) );
-      f.nw[a] = make_float2( float( n[0][3] ), float( n[1][3] ) );
-      const double inflate = 1.0 + 1.0 / 1048576.0;
-      f.rho[a] = make_float2( roundUp( sqrt( n[0][0] * n[0][0] + n[0][1] * n[0][1] + n[0][2] * n[0][2] ) * inflate ),
-                              roundUp( sqrt( n[1][0] * n[1][0] + n[1][1] * n[1][1] + n[1][2] * n[1][2] ) * inflate ) );
+      f.rhoN[a] = roundUp( sqrt( nN[0] * nN[0] + nN[1] * nN[1] + nN[2] * nN[2] ) * inflate );
+      f.rhoP[a] = roundUp( sqrt( nP[0] * nP[0] + nP[1] * nP[1] + nP[2] * nP[2] ) * inflate );
     }
-    double q[4];
-    for ( int r = 0; r < 4; ++r ) q[r] = marginScale * ( fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] ) ) / 131072.0;
-    f.q = make_float4( roundUp( ( q[0] + q[1] ) + ( q[2] + q[3] ) ), 0.0f, 0.0f, 0.0f );
+    double q = 0.0;
+    for ( int r = 0; r < 4; ++r ) q += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
+    f.q = roundUp( marginScale * q / 131072.0 );
+    f.pad = 0.0f;
+    memcpy( f.rows, vp, 64 );
   }
 
   template <int NV>

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--fma", type=int, default=0)
     ap.add_argument("--changed", type=int, default=1)
+    ap.add_argument("--filter", type=int, default=1, help="multi-view filter (DPCU_CULL_OPT_FILTER)")
     ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
     ap.add_argument("--flush", type=int, default=0, help="1: write 256 MiB between iterations (cold L2)")
     a = ap.parse_args()
@@ -34,6 +35,7 @@ def main():
     ctx.set_option(capi.OPT_CTAS_PER_SM, a.ctas)
     ctx.set_option(capi.OPT_FMA, a.fma)
     ctx.set_option(capi.OPT_CHANGED_LIST, a.changed)
+    ctx.set_option(capi.OPT_FILTER, a.filter)
     res = [ctx.result_create() for _ in range(a.views)]
     cams = np.concatenate([scenes.cube_map_cameras(), scenes.cube_map_cameras((50.0, 20.0, -30.0))]) if a.views > 1 else None
     s = capi.Stream()
