@@ -455,7 +455,8 @@ def run_ours(args, rank, world, local_rank):
     sampler.mark("timed1")
     launches1 = ctx.launches() + (tree.launches() if tree else 0)
     headline_kernel = ctx.get_option(capi.OPT_LAST_KERNEL)       # which exact form AUTO picked for the timed steps
-    k_ms, k_n = ctx.kernel_time()
+    k_each = ctx.kernel_times()                                  # per-launch device time of the cull kernel (CUDA events)
+    k_ms, k_n = float(k_each.sum()), len(k_each)
     changed = [r.changed_count() for r in results]
 
     if dist is not None:
@@ -559,6 +560,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n),
+                "launch_ms_p10_p50_p90": [float(x) for x in np.percentile(k_each, [10, 50, 90])] if len(k_each) else None,
                 "step_share": k_ms / ms_total if ms_total else None}
     if tree is not None:
         upper = sum(C3_LEVELS[:-1])

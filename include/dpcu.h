@@ -248,6 +248,8 @@ int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);
  * compaction around it) since the last call, measured with CUDA events on the launching stream;
  * synchronises those events and resets the accumulator.  This is the number bench.py's roofline uses. */
 int dpcuCullGetKernelTime(dpcuCull *ctx, double *totalMs, uint64_t *launches);
+/* the same per launch (oldest first, up to `capacity` entries; *launches = how many there were); also resets */
+int dpcuCullGetKernelTimes(dpcuCull *ctx, float *perLaunchMs, size_t capacity, size_t *launches);
 /* Diagnostics for tests/test_sass.py (no device needed): byte offsets, inside the cull kernels' parameter block
  * for nViews views, of the (1.0f, 1.0f) multiplier, the view-projection rows and the filter constants, so that the
  * SASS check can tell the reference arithmetic (products of view-projection entries must never be contracted into

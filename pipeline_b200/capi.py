@@ -136,6 +136,7 @@ def _declare(L):
         "dpcuCullGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
         "dpcuDebugKernelArgLayout": [C.c_int, _szp, _szp, _szp, _szp],
         "dpcuCullGetKernelTime": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
+        "dpcuCullGetKernelTimes": [_vp, _f32p, C.c_size_t, _szp],
         "dpcuCullResultSetPeerBits": [_vp, C.POINTER(_vp), C.c_int, C.c_size_t],
         "dpcuCullResultBuildVisibleList": [_vp, _vp],
         "dpcuCullResultVisibleDevicePointers": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
@@ -515,6 +516,13 @@ class Cull:
         ms, n = C.c_double(), C.c_uint64()
         check(lib().dpcuCullGetKernelTime(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def kernel_times(self, capacity=4096):
+        """per-launch ms of the cull kernel since the last call (oldest first); needs OPT_PROFILE = 1."""
+        out = np.zeros(capacity, np.float32)
+        n = C.c_size_t()
+        check(lib().dpcuCullGetKernelTimes(self.h, out.ctypes.data_as(_f32p), capacity, C.byref(n)))
+        return out[:min(n.value, capacity)].copy()
 
     def close(self):
         if self.h:

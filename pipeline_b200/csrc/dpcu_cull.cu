@@ -2226,6 +2226,23 @@ extern "C"
     return DPCU_OK;
   }
 
+  int dpcuCullGetKernelTimes( dpcuCull *ctx, float *perLaunchMs, size_t capacity, size_t *launches )
+  {
+    DPCU_REQUIRE( ctx && launches && ( perLaunchMs || !capacity ), "NULL argument" );
+    dpcu::DeviceGuard guard( ctx->device );
+    size_t n = 0;
+    for ( size_t i = 0; i + 1 < ctx->profUsed; i += 2, ++n )
+    {
+      DPCU_CUDA( cudaEventSynchronize( ctx->profEvents[i + 1] ) );
+      float ms = 0.f;
+      DPCU_CUDA( cudaEventElapsedTime( &ms, ctx->profEvents[i], ctx->profEvents[i + 1] ) );
+      if ( n < capacity ) perLaunchMs[n] = ms;
+    }
+    *launches = n;
+    ctx->profUsed = 0;
+    return DPCU_OK;
+  }
+
   int dpcuDebugKernelArgLayout( int nViews, size_t *onePairOffset, size_t *viewProjectionOffset, size_t *filterOffset, size_t *totalBytes )
   {
     DPCU_REQUIRE( nViews >= 1 && nViews <= DPCU_MAX_VIEWS, "nViews must be 1..DPCU_MAX_VIEWS" );
