@@ -1,0 +1,231 @@
+// Compaction of the changed / visible lists, object and matrix bookkeeping kernels, K4 (group bounding box).
+#pragma once
+
+namespace dpcu
+{
+  // ------------------------------------------------------------------------------------------
+  // Ordered changed list.  One CTA per 8192-object segment and view: seg[] already holds the
+  // exclusive prefix, so the CTA only block-scans the popcounts of its 256 flipped-bit words and
+  // expands them; ascending group index order falls out of the layout (BitArray::traverseBits
+  // order, dp/util/BitArray.h:127-136).
+  struct CompactArgs
+  {
+    uint32_t const *chg[DPCU_MAX_VIEWS];
+    uint32_t const *prefix[DPCU_MAX_VIEWS];
+    uint32_t       *changed[DPCU_MAX_VIEWS];
+    uint32_t       *hostChanged[DPCU_MAX_VIEWS];    // optional mirror of the list in pinned host memory ...
+    uint32_t       *hostCount[DPCU_MAX_VIEWS];      // ... and of its length
+    uint32_t        hostCapacity[DPCU_MAX_VIEWS];
+    uint32_t        nWords;
+    uint32_t        nSegs;
+  };
+
+  __global__ void __launch_bounds__( 256 ) compactChangedKernel( const __grid_constant__ CompactArgs a )
+  {
+    const uint32_t v    = blockIdx.y;
+    const uint32_t s    = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t base0 = a.prefix[v][s];
+    const uint32_t count = a.prefix[v][s + 1] - base0;
+    if ( s == 0 && threadIdx.x == 0 && a.hostCount[v] ) *a.hostCount[v] = a.prefix[v][a.nSegs];
+    if ( count == 0 ) return;                        // nothing changed in this segment
+
+    // the segment's indices are expanded into shared memory first, so that the list (and its host
+    // mirror, over PCIe) is written as one contiguous, coalesced run per segment
+    __shared__ uint32_t sIdx[1u << kSegObjectsLog2];
+    __shared__ uint32_t sWarp[8];
+    const uint32_t w = s * kSegWords + threadIdx.x;
+    uint32_t c = ( w < a.nWords ) ? a.chg[v][w] : 0u;
+    const uint32_t pc = __popc( c );
+    uint32_t incl = pc;
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 )
+    {
+      uint32_t t = __shfl_up_sync( 0xffffffffu, incl, d );
+      if ( lane >= d ) incl += t;
+    }
+    if ( lane == 31 ) sWarp[warp] = incl;
+    __syncthreads();
+    uint32_t off = incl - pc;
+    for ( uint32_t k = 0; k < warp; ++k ) off += sWarp[k];
+    const uint32_t base = w << 5;
+    while ( c )
+    {
+      const uint32_t b = __ffs( c ) - 1;
+      sIdx[off++] = base + b;
+      c &= c - 1;
+    }
+    __syncthreads();
+    uint32_t *out = a.changed[v] + base0;
+    uint32_t *host = a.hostChanged[v];
+    const uint32_t hostRoom = a.hostCapacity[v] > base0 ? a.hostCapacity[v] - base0 : 0u;
+    for ( uint32_t k = threadIdx.x; k < count; k += 256 )
+    {
+      const uint32_t x = sIdx[k];
+      out[k] = x;
+      if ( host && k < hostRoom ) host[base0 + k] = x;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Visible-instance list (the consumer of the result stays on the GPU).
+  // Per-segment popcounts of the visibility words, scanned by the last CTA exactly like the
+  // changed counts; compactChangedKernel then expands bits[] instead of chg[].
+  __global__ void __launch_bounds__( kCullThreads ) segmentPopcountKernel( uint32_t const *bits, uint32_t nWords, uint32_t nSegs,
+                                                                          uint32_t *seg, uint32_t *prefix, uint32_t *done )
+  {
+    __shared__ uint32_t sPart[kCullThreads / 32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for ( uint32_t s = blockIdx.x; s < nSegs; s += gridDim.x )
+    {
+      const uint32_t w = s * kSegWords + threadIdx.x;
+      uint32_t pc = ( w < nWords ) ? __popc( bits[w] ) : 0u;
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 ) pc += __shfl_xor_sync( 0xffffffffu, pc, d );
+      if ( lane == 0 ) sPart[warp] = pc;
+      __syncthreads();
+      if ( threadIdx.x == 0 )
+      {
+        uint32_t total = 0;
+        for ( int k = 0; k < kCullThreads / 32; ++k ) total += sPart[k];
+        seg[s] = total;
+      }
+      __syncthreads();
+    }
+    ViewOut out[1];
+    out[0].seg = seg;
+    out[0].prefix = prefix;
+    scanSegmentsInLastCta<1>( out, nSegs, done );
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // object upload: pack transformIndex into lower.w, zero extent.w, track the largest index
+  __global__ void packObjectsKernel( float4 const *lower, float4 const *extent, uint32_t const *tidx, uint32_t n,
+                                     float4 *lowerIdx, float4 *extentOut, uint32_t *maxIndex )
+  {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;
+    if ( i < n )
+    {
+      float4 lo = lower[i];
+      float4 ex = extent[i];
+      uint32_t t = tidx ? tidx[i] : __float_as_uint( lo.w );
+      lo.w = __uint_as_float( t );
+      ex.w = 0.0f;
+      lowerIdx[i]  = lo;
+      extentOut[i] = ex;
+      m = t;
+    }
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 ) m = max( m, __shfl_xor_sync( 0xffffffffu, m, d ) );
+    if ( ( threadIdx.x & 31 ) == 0 && m ) atomicMax( maxIndex, m );
+  }
+
+  // matrices[indices[k]] = packed[k]
+  __global__ void scatterMatricesKernel( uint32_t const *indices, float4 const *packed, uint32_t n, float4 *mats )
+  {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per matrix row
+    if ( t < n * 4u ) mats[4ull * indices[t >> 2] + ( t & 3u )] = packed[t];
+  }
+
+  // strided device -> packed device copy (device-side groupSetMatrices with stride != 64)
+  __global__ void gatherStridedKernel( char const *src, size_t stride, uint32_t count, float *dst )
+  {
+    size_t t = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;   // one thread per float
+    if ( t < size_t( count ) * 16 ) dst[t] = *reinterpret_cast<float const *>( src + ( t >> 4 ) * stride + ( t & 15 ) * 4 );
+  }
+
+  // ResultBitSet incarnation step (dp/culling/src/ResultBitSet.cpp:65-79): bits of objects
+  // [oldN, newN) become 1, bits >= newN become 0, older bits are kept.
+  __global__ void resizeBitsKernel( uint32_t *bits, uint32_t oldN, uint32_t newN, uint32_t capWords )
+  {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( w >= capWords ) return;
+    const uint64_t lo = uint64_t( w ) << 5, hi = lo + 32;
+    if ( hi <= oldN && hi <= newN ) return;
+    uint32_t x = bits[w];
+    uint32_t keep  = ( lo >= oldN ) ? 0u : ( hi <= oldN ? ~0u : ( ~0u >> ( 32 - ( oldN - lo ) ) ) );   // bits < oldN
+    uint32_t valid = ( lo >= newN ) ? 0u : ( hi <= newN ? ~0u : ( ~0u >> ( 32 - ( newN - lo ) ) ) );   // bits < newN
+    x = ( ( x & keep ) | ~keep ) & valid;
+    bits[w] = x;
+  }
+
+  // ResultBitSet::onNotify (dp/culling/src/ResultBitSet.cpp:110-128)
+  __global__ void moveBitKernel( uint32_t *bits, uint32_t size, uint32_t oldIndex, uint32_t newIndex, uint32_t *mirror )
+  {
+    if ( newIndex < size )
+    {
+      uint32_t value = 1u;
+      if ( oldIndex < size ) value = ( bits[oldIndex >> 5] >> ( oldIndex & 31 ) ) & 1u;
+      uint32_t w = bits[newIndex >> 5];
+      w = value ? ( w | ( 1u << ( newIndex & 31 ) ) ) : ( w & ~( 1u << ( newIndex & 31 ) ) );
+      bits[newIndex >> 5] = w;
+      if ( mirror ) mirror[newIndex >> 5] = w;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // K4: group bounding box, ManagerBitSet::calculateBoundingBox scalar branch
+  // (dp/culling/src/ManagerBitSet.cpp:268-306).  min/max are order independent, so a tree
+  // reduction gives the reference's sequential Box4f::update result bit for bit, except that
+  // Boxnt::update skips NaN coordinates (both comparisons false) - fminf/fmaxf do the same.
+  // Signed zeros: update() keeps the first of +0/-0 it met; the final box is compared with ==
+  // semantics by every consumer, and the test-suite compares with np.array_equal (-0 == +0).
+  struct BoxAcc
+  {
+    float lo[3], hi[3];
+  };
+
+  __device__ __forceinline__ void boxUpdate( BoxAcc &b, float4 p )
+  {
+    b.lo[0] = fminf( b.lo[0], p.x ); b.hi[0] = fmaxf( b.hi[0], p.x );
+    b.lo[1] = fminf( b.lo[1], p.y ); b.hi[1] = fmaxf( b.hi[1], p.y );
+    b.lo[2] = fminf( b.lo[2], p.z ); b.hi[2] = fmaxf( b.hi[2], p.z );
+  }
+
+  __device__ __forceinline__ uint32_t orderedKey( float f )
+  {
+    uint32_t u = __float_as_uint( f );
+    return ( u & 0x80000000u ) ? ~u : ( u | 0x80000000u );
+  }
+
+  __global__ void __launch_bounds__( 256 ) boundingBoxKernel( float4 const *lowerIdx, float4 const *extent,
+                                                              float4 const *mats, uint32_t n, uint32_t *keys /* 3 min, 3 max */ )
+  {
+    const float FMAX = 3.402823466e+38f;
+    BoxAcc b = { { FMAX, FMAX, FMAX }, { -FMAX, -FMAX, -FMAX } };
+    for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+    {
+      const float4 lo = ldStream( lowerIdx + i );
+      const float4 ex = ldStream( extent + i );
+      float4 const *m = mats + 4ull * __float_as_uint( lo.w );
+      const Obb o = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, __ldg( m ), __ldg( m + 1 ), __ldg( m + 2 ), __ldg( m + 3 ) );
+      const float4 v0 = o.pt;
+      const float4 v1 = add4( v0, o.ax );
+      const float4 v2 = add4( v0, o.ay );
+      const float4 v3 = add4( v1, o.ay );
+      boxUpdate( b, v0 ); boxUpdate( b, v1 ); boxUpdate( b, v2 ); boxUpdate( b, v3 );
+      boxUpdate( b, add4( v0, o.az ) ); boxUpdate( b, add4( v1, o.az ) );
+      boxUpdate( b, add4( v2, o.az ) ); boxUpdate( b, add4( v3, o.az ) );
+    }
+#pragma unroll
+    for ( int k = 0; k < 3; ++k )
+    {
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 )
+      {
+        b.lo[k] = fminf( b.lo[k], __shfl_xor_sync( 0xffffffffu, b.lo[k], d ) );
+        b.hi[k] = fmaxf( b.hi[k], __shfl_xor_sync( 0xffffffffu, b.hi[k], d ) );
+      }
+    }
+    if ( ( threadIdx.x & 31 ) == 0 )
+    {
+#pragma unroll
+      for ( int k = 0; k < 3; ++k )
+      {
+        atomicMin( keys + k, orderedKey( b.lo[k] ) );
+        atomicMax( keys + 3 + k, orderedKey( b.hi[k] ) );
+      }
+    }
+  }
+}
