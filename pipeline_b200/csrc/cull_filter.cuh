@@ -26,15 +26,18 @@
 //   arithmetic adds less than another 8u S.  The margin used is 2^-17 S' with
 //   S' = max_r (|p_r| + |a_r| + |b_r| + |c_r|) * sum_r sum_c |P[r][c]| >= S  (at least 8x the sum of the two
 //   errors; one multiply per object and view); supports are bounded by Cauchy-Schwarz with radius and plane
-//   norms rounded up.  A decision is taken
-//   only when a comparison is TRUE, so NaN never decides, and only when S < 2^96 (nothing
-//   overflowed).  Everything else - and every warp that holds a non-affine object or a
-//   non-finite view-projection - takes the reference arithmetic of cull_views.cuh.
+//   norms rounded up.  The centre values come from the centre's clip coordinates (A_x, A_y, A_z, W) =
+//   centre * P:  fN_a = W + A_a,  fP_a = W - A_a,  so (V) reads  W - max_a |A_a| > margin.
+//   A decision is taken only when a comparison is TRUE and only when S' < 2^96 (nothing overflowed,
+//   every intermediate is finite - so neither a NaN comparison nor a NaN dropped by fmin / fmax can
+//   decide).  Everything else - and every warp that holds a non-affine object or a non-finite
+//   view-projection - takes the reference arithmetic of cull_views.cuh.
 //
-// The undecided pairs of a warp's 32 objects x NV views are gathered into dense batches of 32
-// (pair -> lane), their OBBs fetched with shuffles and their view-projection rows from a small
-// shared-memory table, evaluated with the exact packed arithmetic, and scattered back into the
-// per-view ballot words with warp OR-reductions.
+// The undecided pairs of a warp's 32 objects x NV views are queued in shared memory and gathered into
+// dense batches of 32 (pair -> lane); their OBBs come back from a per-warp shared-memory park (which
+// also frees the OBB registers during classification), their view-projection rows from a small
+// shared-memory table; they are evaluated with the exact packed arithmetic and scattered back into
+// the per-view ballot words with warp OR-reductions.
 #pragma once
 
 #include "cull_views.cuh"
