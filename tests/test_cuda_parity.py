@@ -584,63 +584,20 @@ def test_peer_bitset_gather_in_kernel_epilogue(capi, port, nv):
 
 
 # ------------------------------------------------------------------ the multi-view filter (cull_filter.cuh)
-def _affine_boundary_scene(n, seed):
-    """Affine objects (the filter only engages on them) built to sit ON the decision boundaries: integer / half
-    translations and extents under projections with small integer entries (corners exactly on x = +-w), boxes as
-    large as the frustum, boxes straddling the eye, zero extents, negative and wildly different scales."""
-    rng = np.random.RandomState(seed)
-    half = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 8.0], np.float32)
-    lower4 = np.zeros((n, 4), np.float32)
-    upper4 = np.zeros((n, 4), np.float32)
-    lo = -rng.choice(half, size=(n, 3))
-    ex = rng.choice(half, size=(n, 3)) + rng.choice(half, size=(n, 3))
-    big = rng.rand(n) < 0.1                                   # boxes of the size of the scene
-    ex[big] *= 16.0
-    lower4[:, :3], upper4[:, :3] = lo, lo + ex
-    lower4[:, 3] = upper4[:, 3] = 1.0
-    mats = np.zeros((n, 4, 4), np.float32)
-    scale = rng.choice(np.array([1.0, -1.0, 0.5, 2.0, 0.0, 1e-20, 1e12, 3.0], np.float32), size=(n, 3),
-                       p=[0.4, 0.1, 0.1, 0.1, 0.05, 0.05, 0.05, 0.15])
-    perm = np.array([[0, 1, 2], [1, 2, 0], [2, 0, 1], [0, 2, 1]])[rng.randint(0, 4, size=n)]
-    for r in range(3):
-        mats[np.arange(n), r, perm[:, r]] = scale[:, r]      # signed / scaled axis permutations: exact arithmetic
-    shear = rng.rand(n) < 0.3
-    mats[shear, 0, 1] = rng.choice(np.array([0.5, -0.5, 1.0], np.float32), size=int(shear.sum()))
-    rot = rng.rand(n) < 0.3                                   # and a share of generic rotations
-    ang = rng.rand(n).astype(np.float32) * 6.28
-    c, s_ = np.cos(ang).astype(np.float32), np.sin(ang).astype(np.float32)
-    mats[rot, 0, 0], mats[rot, 0, 1], mats[rot, 1, 0], mats[rot, 1, 1] = c[rot], s_[rot], -s_[rot], c[rot]
-    mats[rot, 0, 2] = mats[rot, 1, 2] = mats[rot, 2, 0] = mats[rot, 2, 1] = 0.0
-    mats[rot, 2, 2] = 1.0
-    mats[:, 3, :3] = rng.randint(-24, 25, size=(n, 3)).astype(np.float32) * rng.choice(np.array([0.5, 1.0, 1.0, 4.0], np.float32), size=(n, 1))
-    mats[:, 3, 3] = 1.0
-    extent4 = np.zeros((n, 4), np.float32)
-    extent4[:, :3] = upper4[:, :3] - lower4[:, :3]
-    return lower4, extent4, mats, np.arange(n, dtype=np.uint32)
-
-
-def _boundary_views():
-    persp = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, -1, -1], [0, 0, -2, 0]], np.float32)        # w = -z, z' = -z - 2: integer planes
-    ortho = np.eye(4, dtype=np.float32)                                                               # w = 1: the unit cube
-    ortho8 = np.diag(np.array([0.125, 0.125, 0.125, 1.0], np.float32))                                # the cube [-8, 8]^3
-    behind = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, -2, 0]], np.float32)         # the same looking down +z
-    shifted = persp.copy()
-    shifted[3] = [2.0, -3.0, 0.0, 16.0]                                                               # eye moved, integer entries
-    frustum = scenes.mat_mul(scenes.make_look_at((0, 0, 20), (0, 0, 0), (0, 1, 0)), scenes.make_frustum(-0.5, 0.5, -0.5, 0.5, 1.0, 40.0))
-    cube = scenes.cube_map_cameras((1.0, 2.0, 3.0))
-    return np.ascontiguousarray(np.stack([persp, ortho, ortho8, behind, shifted, frustum, cube[0], cube[3]]), np.float32)
-
-
 @pytest.mark.parametrize("kernel", ["auto", "views", "lines"])
 @pytest.mark.parametrize("seed", [101, 102, 103])
-def test_filter_decisions_on_the_boundaries(capi, port, kernel, seed):
+def test_filter_decisions_on_the_boundaries(capi, port, golden, kernel, seed):
     """The filter may only decide what it can prove.  A scene where a large share of the (object, view) pairs
     lies exactly on or near a clip plane, eight views at once (up to 256 undecided pairs per warp step: several
     gather batches), filter on and off: identical to the oracle bit for bit, both ways."""
     n = 40000 + 37
-    lower4, extent4, mats, tidx = _affine_boundary_scene(n, seed)
-    vps = _boundary_views()
+    lower4, extent4, mats, tidx = cases.affine_boundary_scene(n, seed)
+    vps = cases.boundary_views()
     want = [port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vps[v]) for v in range(8)]
+    if seed == 101:                                          # this scene's answers also exist from the compiled reference
+        g = golden("boundary40k")
+        for v in range(8):
+            assert np.array_equal(want[v], g["bits%d" % v]), v
     share = [popcount(w) / n for w in want]
     assert min(share) > 0.0 and max(share) < 1.0             # every view really splits the scene
     for nv in (8, 5, 2):

@@ -72,6 +72,16 @@ def test_special_values(port, golden):
         assert np.array_equal(changed, g["changed%d" % k])
 
 
+def test_boundary_scene_eight_views(port, golden):
+    """the multi-view filter's adversarial scene (objects sitting on the clip planes): the restatement equals the
+    compiled reference's answers for all eight views"""
+    g = golden("boundary40k")
+    lower4, extent4, mats, tidx = cases.affine_boundary_scene(40037, 101)
+    vps = cases.boundary_views()
+    for v in range(8):
+        assert np.array_equal(port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vps[v]), g["bits%d" % v]), v
+
+
 def test_gather_and_stride(port, golden):
     g = golden("gather5k")
     lower4, extent4, upper4, raw, tidx, stride = cases.gather_case()
