@@ -310,3 +310,30 @@ def test_transform_tree_feeds_cuda_manager_zero_copy(dropin):
 
     _drive_trees([ref_tree, dev_tree], check)
     cpu.close(), gpu.close(), ref_tree.close(), dev_tree.close()
+
+
+# ------------------------------------------------------------------ the same, as the reference's own C++ would write it
+FRAME_LOOP = os.path.join(ROOT, "tests", "cpp", "_build", "frame_loop")
+
+
+def test_cpp_frame_loop_fails_loudly_without_gpu(dropin):
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not os.path.exists(FRAME_LOOP):
+        pytest.skip("tests/cpp/_build/frame_loop not present")
+    r = subprocess.run([FRAME_LOOP], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_frame_loop_reference_stack_vs_cuda_stack(dropin):
+    """tests/cpp/frame_loop.cpp: dp::transform::Tree + dp::culling::cpu::Manager next to dp::transform::cuda::Tree +
+    dp::culling::cuda::Manager, driven by plain C++ exactly as xbar drives them; six frames, everything identical."""
+    import subprocess
+    if not os.path.exists(FRAME_LOOP):
+        pytest.skip("tests/cpp/_build/frame_loop not present (built only where /root/reference exists)")
+    r = subprocess.run([FRAME_LOOP], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ok") and r.stdout.count("identical") == 6, r.stdout
