@@ -798,6 +798,35 @@ def test_visible_list_is_the_ascending_set_bits(capi, port, n):
     r.close(), ctx.close()
 
 
+def test_profiling_and_kernel_choice_queries(capi):
+    """DPCU_CULL_OPT_PROFILE / dpcuCullGetKernelTime(s) / DPCU_CULL_OPT_LAST_KERNEL: what bench.py's roofline uses"""
+    n = 70000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    ctx.set_option(capi.OPT_PROFILE, 1)
+    r = ctx.result_create()
+    for vp in cases.frames(4):
+        ctx.run([r], vp)
+    assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_DIRECT          # a small group, one view
+    each = ctx.kernel_times()
+    assert len(each) == 4 and (each > 0).all() and (each < 50.0).all()
+    assert len(ctx.kernel_times()) == 0                                         # reading resets
+    ctx.run([r], cases.frames(1)[0])
+    total, launches = ctx.kernel_time()
+    assert launches == 1 and 0.0 < total < 50.0
+    res3 = [ctx.result_create() for _ in range(3)]
+    ctx.run(res3, _views_for(3))
+    assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_VIEWS
+    ctx.set_option(capi.OPT_KERNEL, capi.KERNEL_LINES)
+    ctx.run(res3, _views_for(3))
+    assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_LINES
+    for x in res3 + [r]:
+        x.close()
+    ctx.close()
+
+
 # ------------------------------------------------------------------ dp/cuda layer
 def test_buffers_streams_events(capi):
     s = capi.Stream()
