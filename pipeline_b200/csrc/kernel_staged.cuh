@@ -48,6 +48,9 @@ namespace dpcu
   cullStagedKernel( const __grid_constant__ CullArgs<NV> a )
   {
     extern __shared__ __align__( 128 ) unsigned char smemRaw[];
+    __shared__ f32x2 sP[NV * 8];
+    __shared__ FilterScratch<NV> sScratch[kCullThreads / 32];
+    if ( NV > 1 ) fillViewTable<NV>( sP, a );
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     WarpRing &ring = reinterpret_cast<WarpRing *>( smemRaw )[warp];
 
@@ -151,8 +154,15 @@ namespace dpcu
       {
         const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
         const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
-        const ObbPairs ob = broadcastObb( obb );
-        myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+        if ( fast && a.useFilter )
+        {
+          myWord = cullViewsFiltered<NV>( obb, a.filter, sP, sScratch[threadIdx.x >> 5], a.onePair, live, lane );
+        }
+        else
+        {
+          const ObbPairs ob = broadcastObb( obb );
+          myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+        }
       }
       if ( lane < NV ) storeWord<NV>( a.out[lane], a, tile0, myWord, old0 );
       tile0 = tile1; tile1 = tile2;
