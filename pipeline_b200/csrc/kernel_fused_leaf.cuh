@@ -36,6 +36,9 @@ namespace dpcu
   cullFusedLeafKernel( const __grid_constant__ CullArgs<NV> a, const __grid_constant__ LeafArgs t )
   {
     __shared__ float4 sTranspose[kCullThreads / 32][2][128];     // per warp: locals in, worlds out (2 KiB each)
+    __shared__ f32x2 sP[NV > 1 ? NV * 8 : 1];
+    __shared__ FilterScratch<NV> sScratch[NV > 1 ? kCullThreads / 32 : 1];
+    if ( NV > 1 ) fillViewTable<NV>( sP, a );
     const uint32_t lane   = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * kCullThreads;
     float4 *bufIn = sTranspose[threadIdx.x >> 5][0], *bufOut = sTranspose[threadIdx.x >> 5][1];
@@ -138,8 +141,15 @@ namespace dpcu
       {
         const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
         const bool fast   = __all_sync( 0xffffffffu, affine ) && a.vpFinite;
-        const ObbPairs ob = broadcastObb( obb );
-        myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+        if ( fast && a.useFilter )
+        {
+          myWord = cullViewsFiltered<NV>( obb, a.filter, sP, sScratch[threadIdx.x >> 5], a.onePair, live, lane );
+        }
+        else
+        {
+          const ObbPairs ob = broadcastObb( obb );
+          myWord = fast ? cullViews<NV, true>( ob, a.vp, a.onePair, live, lane ) : cullViews<NV, false>( ob, a.vp, a.onePair, live, lane );
+        }
       }
       if ( lane < NV && ( i - lane ) < a.n ) storeWord<NV>( a.out[lane], a, word, myWord, oldBits );
       ent = entN; entN = entNN; dirty = dirtyN;
