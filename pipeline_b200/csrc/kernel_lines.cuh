@@ -138,9 +138,10 @@ namespace dpcu
   // measured at 64 Mi objects before the filter: 2 views 1.55 / 1.23 / 1.16 ms and 6 views 2.82 / 2.61 / 2.64 ms at
   // 2 / 3 / 4 CTAs per SM;
   // with the filter (fewer issue slots, more waiting on memory) 4 CTAs per SM win for every multi-view count:
-  // 6 views 2.068 ms at 3 CTAs (80 registers) -> 1.937 ms at 4 (64 registers, ~70 bytes of spills)
+  // 6 views 2.068 ms at 3 CTAs (80 registers) -> 1.937 ms at 4 (64 registers, ~70 bytes of spills); the 2-view
+  // instantiation is close to the HBM bound and prefers no spills: 1.154 ms at 4 CTAs, 1.103 ms at 3, 1.289 ms at 5
   template <int NV, bool kFuseList>
-  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : 4 )
+  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : ( NV == 2 ? 3 : 4 ) )
   cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane   = threadIdx.x & 31u;
