@@ -759,7 +759,11 @@ extern "C"
     // can the last level run inside the cull kernel?  object i <-> entry i of that level
     bool fuse = false;
     size_t lastFirst = 0;
-    if ( levels >= 1 && ctx->n && ctx->optFuseLeaf && !ctx->optFma )
+    // peer bitsets (multi-GPU gather) are stored by the line-granular kernel: with peers the tree is propagated
+    // level by level and the cull follows as its own launch
+    bool peers = false;
+    if ( results ) for ( int v = 0; v < nViews && v < DPCU_MAX_VIEWS; ++v ) peers = peers || ( results[v] && results[v]->nPeers > 0 );
+    if ( levels >= 1 && ctx->n && ctx->optFuseLeaf && !ctx->optFma && !peers )
     {
       lastFirst = tree->levelOffsets[levels - 1];
       const size_t lastCount = tree->levelOffsets[levels] - lastFirst;

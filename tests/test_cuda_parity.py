@@ -765,6 +765,44 @@ def test_host_mirror_capacity_and_errors(capi, port):
     r.close(), ctx.close(), m.close(), small.close()
 
 
+def test_run_with_tree_and_peer_bitsets(capi, port):
+    """C3 on several GPUs: with peer bitsets set, dpcuCullRunWithTree propagates the whole tree and hands the cull
+    to the line-granular kernel (which stores the lines into the peers) instead of fusing the leaf level."""
+    levels = (4, 32, 1024)
+    entries, offsets, n_nodes = scenes.hierarchy_topology(levels)
+    n = levels[-1]
+    first_leaf = n_nodes - n
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=0)
+    lower4, extent4, upper4, _, _ = cases.random_case(n)
+    tidx = np.arange(first_leaf, n_nodes, dtype=np.uint32)
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    t.set_locals(0, local)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    r = ctx.result_create()
+    words = (n + 31) // 32
+    full = capi.Buffer(((words + 31) // 32) * 128 + 4096)
+    full.fill(0)
+    r.set_peer_bits([full.ptr], 1024 // 32)                  # this shard starts at object 1024 of the full bitset
+    view = scenes.make_look_at((0, 0, 150), (0, 0, 0), (0, 1, 0))
+    vp = scenes.mat_mul(view, scenes.make_perspective(40.0, 1.3, 1.0, 500.0))
+    ctx.run_with_tree(t, [r], vp)
+    assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_LINES
+    world = np.zeros_like(local)
+    world[0] = np.eye(4, dtype=np.float32)
+    nw = (n_nodes + 31) // 32
+    port.tree_compute(local, world, entries, offsets, np.full(nw, 0xFFFFFFFF, np.uint32), np.zeros(nw, np.uint32))
+    want = port.cull_bits(lower4, extent4, tidx, world.reshape(-1), vp)
+    assert np.array_equal(r.bits(), want)
+    got = np.zeros(32 + words, np.uint32)
+    full.download(got)
+    assert np.array_equal(got[32:32 + words], want) and not got[:32].any()
+    r.close(), ctx.close(), t.close(), full.close()
+
+
 # ------------------------------------------------------------------ visible-instance list built on the device
 @pytest.mark.parametrize("n", [0, 1, 33, 8191, 8192, 8193, 100003])
 def test_visible_list_is_the_ascending_set_bits(capi, port, n):
