@@ -194,9 +194,10 @@ int dpcuCullResultGetVisible(dpcuCullResult *result, uint32_t *hostIndices, size
 /* Result mirror in pinned host memory.  The reference's Result lives in host memory
  * (ResultBitSet::m_results / m_changedObjects, dp/culling/ResultBitSet.h:57-61); with a mirror the
  * cull writes the visibility words and the changed list straight into the caller's pinned,
- * device-mapped buffers (dpcuHostBufferCreate) over PCIe while it runs - whole 128-byte lines from
- * the cull kernel's epilogue, contiguous runs from the compaction kernel - so that after
- * dpcuCullResultSynchronize the result is readable on the host without any further copy:
+ * device-mapped buffers (dpcuHostBufferCreate) over PCIe while it runs - whole 128-byte bitset lines
+ * and coalesced runs of the changed list from the line-granular cull kernel (large groups), or a copy /
+ * the compaction kernel's stores queued behind the other kernel forms - so that after
+ * dpcuCullResultSynchronize the result is readable on the host without any further call:
  *   hostBits[0 .. ceil(n/32))            visibility words (nWords = capacity, checked by dpcuCullRun)
  *   *hostChangedCount                    length of the changed list
  *   hostChanged[0 .. min(count, cap))    ascending group indices
