@@ -227,6 +227,9 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 #define DPCU_KERNEL_VIEWS_CHAINS 5      /* the views form with three predicate chains per axis instead of a  */
                                         /* counted compare (the earlier formulation; kept for comparison)    */
 #define DPCU_KERNEL_FUSED_LEAF   6      /* reported by DPCU_CULL_OPT_LAST_KERNEL only (dpcuCullRunWithTree)  */
+#define DPCU_KERNEL_LINES_PAIRS  7      /* >= 2 views: line-granular, two views per packed filter instruction, */
+                                        /* undecided pairs queued across the line's steps, L2 bulk prefetch;   */
+                                        /* what AUTO and peer bitsets use for several views (1 view: = LINES)  */
 #define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */

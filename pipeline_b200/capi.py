@@ -14,13 +14,15 @@ import weakref
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdpcu.so")
+# DPCU_LIB: developer override (tools/ builds tuning variants of the library next to the product one)
+LIB_PATH = os.environ.get("DPCU_LIB") or os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF, OPT_FUSE_LIST, OPT_LAST_KERNEL, OPT_FILTER, OPT_LINE_WORDS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 TREE_OPT_WIDE_MIN_NODES = 1
-KERNEL_NAMES = {1: "cullDirectKernel", 2: "cullStagedKernel", 3: "cullViewsKernel", 4: "cullLinesKernel", 5: "cullViewsKernel", 6: "cullFusedLeafKernel"}
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS, KERNEL_FUSED_LEAF = 0, 1, 2, 3, 4, 5, 6
+KERNEL_NAMES = {1: "cullDirectKernel", 2: "cullStagedKernel", 3: "cullViewsKernel", 4: "cullLinesKernel", 5: "cullViewsKernel", 6: "cullFusedLeafKernel",
+                7: "cullLinesMvKernel"}
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS, KERNEL_FUSED_LEAF, KERNEL_LINES_PAIRS = 0, 1, 2, 3, 4, 5, 6, 7
 MAX_VIEWS = 8
 
 _vp = C.c_void_p

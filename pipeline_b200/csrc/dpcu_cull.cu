@@ -28,10 +28,12 @@
 #include "cull_stage.cuh"
 #include "cull_views.cuh"
 #include "cull_filter.cuh"
+#include "cull_filter_pairs.cuh"
 #include "tree_propagate.cuh"
 #include "dpcu_internal.h"
 #include "dpcu_tree.h"
 
+#include <cmath>
 #include <cstddef>
 #include <new>
 #include <vector>
@@ -42,6 +44,7 @@
 #include "kernel_views.cuh"
 #include "kernel_staged.cuh"
 #include "kernel_lines.cuh"
+#include "kernel_lines_mv.cuh"
 #include "kernel_fused_leaf.cuh"
 #include "kernel_misc.cuh"
 #endif   // !DPCU_FMA_VARIANT
@@ -233,6 +236,46 @@ namespace dpcu
     memcpy( f.rows, vp, 64 );
   }
 
+  // ViewPairFilter entry `half` (0: view u, 1: view v) of one view-projection (cull_filter_pairs.cuh).  `enabled`
+  // false, a non-finite entry, or sum sum |P| outside [2^-100, 2^39] => q = +inf: the filter never decides this view
+  // (below 2^-100 the margin would not cover the absolute error of underflowing products).
+  static float roundAway( double x )
+  {
+    float f = static_cast<float>( x );
+    return ( static_cast<double>( f ) > x ) ? nextafterf( f, -INFINITY ) : f;      // x <= 0: towards -inf
+  }
+  static void fillViewPairFilter( float const *vp, ViewPairFilter &f, int half, bool enabled, double marginScale )
+  {
+    double P[4][4];
+    bool finite = true;
+    for ( int r = 0; r < 4; ++r ) for ( int c = 0; c < 4; ++c )
+    {
+      P[r][c] = vp[4 * r + c];
+      finite = finite && std::isfinite( vp[4 * r + c] );
+      ( half ? f.k[4 * r + c].y : f.k[4 * r + c].x ) = vp[4 * r + c];
+    }
+    const double inflate = 1.0 + 1.0 / 1048576.0;
+    double q = 0.0;
+    for ( int r = 0; r < 4; ++r ) q += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
+    const bool usable = enabled && finite && q >= 7.888609052210118e-31 /* 2^-100 */ && q <= 549755813888.0 /* 2^39 */;
+    for ( int a = 0; a < 3; ++a )
+    {
+      double nN[3], nP[3];
+      for ( int r = 0; r < 3; ++r )
+      {
+        nN[r] = P[r][a] + P[r][3];          // N plane: x + w
+        nP[r] = P[r][3] - P[r][a];          // P plane: w - x
+      }
+      const float rn = usable ? roundUp( sqrt( nN[0] * nN[0] + nN[1] * nN[1] + nN[2] * nN[2] ) * inflate ) : 0.0f;
+      const float rp = usable ? roundAway( -sqrt( nP[0] * nP[0] + nP[1] * nP[1] + nP[2] * nP[2] ) * inflate ) : 0.0f;
+      ( half ? f.rhoN[a].y : f.rhoN[a].x ) = rn;
+      ( half ? f.nrhoP[a].y : f.nrhoP[a].x ) = rp;
+    }
+    const float rw = usable ? roundAway( -sqrt( P[0][3] * P[0][3] + P[1][3] * P[1][3] + P[2][3] * P[2][3] ) * inflate ) : 0.0f;
+    ( half ? f.nrhoW.y : f.nrhoW.x ) = rw;
+    ( half ? f.q.y : f.q.x ) = usable ? roundUp( marginScale * q / 131072.0 ) : INFINITY;
+  }
+
   template <int NV>
   static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf,
                          bool *mirrorsWritten, bool *listBuilt )
@@ -265,6 +308,17 @@ namespace dpcu
       if ( NV > 1 ) makeViewFilter( vps + 16 * v, args.filter[v], ctx->optFilter == 2 ? 0.125 : ctx->optFilter == 3 ? 0.0 : 1.0 );
     }
     args.useFilter = ( NV > 1 && ctx->optFilter ) ? 1 : 0;
+    args.nMats      = uint32_t( ctx->nMats );
+    args.filterHalf = 0.5f;
+    if ( NV > 1 )
+    {
+      const double scale = ctx->optFilter == 2 ? 0.125 : ctx->optFilter == 3 ? 0.0 : 1.0;
+      for ( int v = 0; v < 2 * ( ( NV + 1 ) / 2 ); ++v )
+      {
+        // an odd view count pads the last pair with a copy of the last view (its result is dropped)
+        fillViewPairFilter( vps + 16 * ( v < NV ? v : NV - 1 ), args.pairFilter[v / 2], v & 1, ctx->optFilter != 0, scale );
+      }
+    }
     // kernel choice: one view is an HBM-bound stream (direct kernel); with more views the cull is
     // issue-bound and the view-sequential packed kernel (cull_views.cuh) is the faster exact form
     const bool peers     = args.nPeers > 0;
@@ -288,7 +342,10 @@ namespace dpcu
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
     args.lineWords = ctx->optLineWords ? uint32_t( ctx->optLineWords ) : 32u;
-    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || autoLines );
+    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || ctx->optKernel == DPCU_KERNEL_LINES_PAIRS || autoLines );
+    // several views: the pair-filter form with the queued exact passes (kernel_lines_mv.cuh), unless the earlier form is asked for
+    const bool useLinesMv = useLines && !leaf && NV >= 2 && ctx->optKernel != DPCU_KERNEL_LINES;
+    if ( useLinesMv ) args.lineWords = 32u;
     *mirrorsWritten = useLines && !leaf;
     const bool fuseList = useLines && !leaf && ctx->optChanged && ctx->optFuseList;
     *listBuilt = fuseList;
@@ -333,6 +390,8 @@ namespace dpcu
     if ( perSm <= 0 )
     {
       if ( useFused ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullFusedLeafKernel<NV>, kCullThreads, 0 );
+      else if ( useLinesMv && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, true>, kCullThreads, 0 );
+      else if ( useLinesMv ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, false>, kCullThreads, 0 );
       else if ( useLines && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, true>, kCullThreads, 0 );
       else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, false>, kCullThreads, 0 );
       else if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
@@ -375,8 +434,10 @@ namespace dpcu
       const uint32_t nLines = uint32_t( divUp( divUp( ctx->n, 32 ), args.lineWords ) );
       const uint32_t ctasForLines = uint32_t( divUp( nLines, kCullThreads / 32 ) );
       if ( uint32_t( grid ) > ctasForLines ) grid = int( ctasForLines );
-      if ( fuseList ) cullLinesKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
-      else            cullLinesKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
+      if ( useLinesMv && fuseList ) cullLinesMvKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
+      else if ( useLinesMv )        cullLinesMvKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
+      else if ( fuseList )          cullLinesKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
+      else                          cullLinesKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
     }
     else if ( ctx->optFma )
@@ -401,7 +462,7 @@ namespace dpcu
     }
     if ( evStop ) DPCU_CUDA( cudaEventRecord( evStop, stream ) );
     ++ctx->launches;
-    ctx->lastKernel = useFused ? DPCU_KERNEL_FUSED_LEAF : useLines ? DPCU_KERNEL_LINES : ctx->optFma ? DPCU_KERNEL_DIRECT
+    ctx->lastKernel = useFused ? DPCU_KERNEL_FUSED_LEAF : useLinesMv ? DPCU_KERNEL_LINES_PAIRS : useLines ? DPCU_KERNEL_LINES : ctx->optFma ? DPCU_KERNEL_DIRECT
                     : useStaged ? DPCU_KERNEL_STAGED : useViews ? ( useChains ? DPCU_KERNEL_VIEWS_CHAINS : DPCU_KERNEL_VIEWS ) : DPCU_KERNEL_DIRECT;
     return DPCU_OK;
   }
@@ -1079,7 +1140,7 @@ extern "C"
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     switch ( option )
     {
-      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( value >= 0 && value <= 5, "kernel must be 0..5" ); ctx->optKernel = value; break;
+      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( ( value >= 0 && value <= 5 ) || value == DPCU_KERNEL_LINES_PAIRS, "kernel must be 0..5 or 7" ); ctx->optKernel = value; break;
       case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;

@@ -44,9 +44,13 @@ namespace dpcu
     unsigned long long onePair;   // (1.0f, 1.0f): runtime multiplier of cull_views.cuh::addProd
     uint32_t      lineWords; // line-granular kernel: bitset words per warp (32 = one 128-byte line; 8 for mid-size groups)
     int           useFilter; // cull_filter.cuh: decide provable (object, view) pairs from centre and radius
+    uint32_t      nMats;     // matrices behind `mats` (bounds the speculative matrix prefetch of kernel_lines_mv.cuh)
     ViewOut       out[NV];
     float4        vp[NV][4];
     ViewFilter    filter[NV];
+    // cull_filter_pairs.cuh (line-granular multi-view kernel): the same filter, two views per packed instruction
+    ViewPairFilter pairFilter[( NV + 1 ) / 2];
+    float         filterHalf;   // 0.5f, as a filter constant (tests/test_sass.py)
   };
 
   // the views' rows as packed pairs in shared memory, for lanes that evaluate different views (cull_filter.cuh)

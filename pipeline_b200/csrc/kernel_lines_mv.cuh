@@ -1,0 +1,257 @@
+// K2, line-granular form for SEVERAL views: the structure of cullLinesKernel (kernel_lines.cuh: a warp owns a
+// 1024-object line of every view's bitset, whole-line stores to the bitset / host mirror / NVLink peers, ordered
+// changed list by decoupled look-back) around a leaner multi-view step:
+//
+//   * the (object, view) pairs are classified two views per packed instruction (cull_filter_pairs.cuh), ~25 warp
+//     instructions per pair instead of ~50;
+//   * the pairs the filter cannot decide (0.9 % on the cube-map scene: 1.8 of the 192 pairs of a 32-object step)
+//     are not evaluated step by step - a step's one or two pairs used to cost a whole 32-lane pass of the reference
+//     arithmetic (~200 instructions, 0.75 passes per step).  They are QUEUED in shared memory across the steps of the
+//     line (the object's OBB once, a 2-byte tag per pair) and evaluated 32 pairs per pass, lane <-> pair, when 32 have
+//     piled up and at the end of the line: ~2.5 passes per 32 steps;
+//   * the line's ballot words live in shared memory (acc[view][step]; the exact passes OR their bits in with shared
+//     atomics), and the previous visibility words are read at the END of the line, so neither costs registers during
+//     the steps: no local-memory traffic (the earlier form ran at 64 registers with 33 LDL + 20 STL);
+//   * every object the filter does not handle - non-affine world matrix, NaN / Inf, a view with a non-finite or
+//     extreme view-projection, the filter switched off - is just an undecided pair: there is ONE copy of the
+//     reference arithmetic in the kernel (the general, non-affine form of cull_views.cuh);
+//   * loads of the NEXT steps are put in flight without registers: one lane asks the TMA unit to pull the next
+//     512-byte runs of lowerIdx / extent into L2 (cp.async.bulk.prefetch.L2), and when the step's transform indices
+//     are consecutive (object i <-> matrix i, the common layout) the 2 KiB of matrices behind them as well.
+#pragma once
+
+namespace dpcu
+{
+#ifndef DPCU_MV_MIN_CTAS
+#define DPCU_MV_MIN_CTAS 4
+#endif
+#ifndef DPCU_MV_PREFETCH
+#define DPCU_MV_PREFETCH 2          // 0: none, 1: per-lane prefetch.global.L2, 2: bulk L2 prefetch by one lane (TMA unit)
+#endif
+#ifndef DPCU_MV_PREFETCH_DIST
+#define DPCU_MV_PREFETCH_DIST 2     // steps ahead
+#endif
+
+  constexpr uint32_t kMvObjCap   = 64;     // queued OBBs: flushed when more than 32 are waiting, a step adds at most 32
+  constexpr uint32_t kMvFlushAt  = 32;     // pairs
+
+  template <int NV>
+  struct MvWarp
+  {
+    float4   obb[4][kMvObjCap];            // pt, ax, ay, az of the queued objects
+    uint32_t acc[NV][32];                  // ballot word of step w for view v
+    uint16_t tag[kMvFlushAt + 32 * NV];    // undecided pairs: object slot << 3 | view
+    uint16_t pos[kMvObjCap];               // step << 5 | lane of the queued object
+  };
+
+  __device__ __forceinline__ void bulkPrefetchL2( void const *p, uint32_t bytes )
+  {
+    asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"( p ), "r"( bytes ) : "memory" );
+  }
+
+  // The reference arithmetic for the queued pairs, 32 per pass (lane <-> pair).
+  template <int NV>
+  __device__ __noinline__ void mvFlush( MvWarp<NV> &sh, f32x2 const *sP, f32x2 one, uint32_t nPairs, uint32_t lane )
+  {
+    __syncwarp();
+    for ( uint32_t base = 0; base < nPairs; base += 32 )
+    {
+      const bool     mine = base + lane < nPairs;
+      const uint32_t tag  = mine ? sh.tag[base + lane] : 0u;
+      const uint32_t view = tag & 7u, slot = tag >> 3;
+      Obb o;
+      o.pt = sh.obb[0][slot]; o.ax = sh.obb[1][slot]; o.ay = sh.obb[2][slot]; o.az = sh.obb[3][slot];
+      const uint32_t pos = sh.pos[slot];
+      ViewPairs P;
+#pragma unroll
+      for ( int k = 0; k < 8; ++k ) P.p[k] = sP[view * 8 + k];
+      const bool visible = cornersVisible<true>( clipVectors<false>( broadcastObb( o ), P, one ) );
+      if ( mine && visible ) atomicOr( &sh.acc[view][pos >> 5], 1u << ( pos & 31u ) );
+    }
+    __syncwarp();
+  }
+
+  template <int NV, bool kFuseList>
+  __global__ void __launch_bounds__( kCullThreads, DPCU_MV_MIN_CTAS )
+  cullLinesMvKernel( const __grid_constant__ CullArgs<NV> a )
+  {
+    constexpr int kPairs = ( NV + 1 ) / 2;
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t below  = ( 1u << lane ) - 1u;
+    const uint32_t nWords = ( a.n + 31u ) >> 5, nLines = ( nWords + 31u ) >> 5;
+    const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
+    uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 );
+    uint32_t pending = kNoLine;
+    __shared__ f32x2 sP[NV * 8];
+    __shared__ MvWarp<NV> sWarp[kCullThreads / 32];
+    MvWarp<NV> &sh = sWarp[threadIdx.x >> 5];
+    fillViewTable<NV>( sP, a );
+    for ( ;; )
+    {
+      if ( kFuseList )
+      {
+        // ascending claims: every predecessor of a claimed line belongs to a warp that is already running
+        uint32_t claimed = 0;
+        if ( lane == 0 ) claimed = atomicAdd( a.chunkCounter, 1u );
+        line = __shfl_sync( 0xffffffffu, claimed, 0 );
+      }
+      if ( line >= nLines ) break;
+      const uint32_t word0 = line << 5, myWord = word0 + lane;
+      const bool     wordLive = myWord < nWords;
+      const uint32_t steps = min( 32u, nWords - word0 );
+      uint32_t nObj = 0, nPairs = 0;                         // queue fill (warp-uniform)
+#if DPCU_MV_PREFETCH
+      {
+        // the first steps of the line
+        const uint32_t i0 = word0 << 5;
+        const uint32_t cnt = min( a.n - i0, 32u * DPCU_MV_PREFETCH_DIST );
+#if DPCU_MV_PREFETCH == 2
+        if ( lane == 0 )
+        {
+          bulkPrefetchL2( a.lowerIdx + i0, cnt * 16u );
+          bulkPrefetchL2( a.extent + i0, cnt * 16u );
+        }
+#else
+        if ( lane < 8u * DPCU_MV_PREFETCH_DIST && lane * 8u < cnt ) prefetchL2( ( ( lane & 1u ) ? a.extent : a.lowerIdx ) + i0 + ( lane >> 1 ) * 8u );
+#endif
+      }
+#endif
+#pragma unroll 1
+      for ( uint32_t w = 0; w < steps; ++w )
+      {
+        const uint32_t i    = ( ( word0 + w ) << 5 ) + lane;
+        const bool     live = i < a.n;
+        const uint32_t liveMask = __ballot_sync( 0xffffffffu, live );
+        Obb obb;
+        obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );   // not affine: never decided, masked by liveMask
+        uint32_t tidx = 0;
+        if ( live )
+        {
+          const float4 lo = ldStream( a.lowerIdx + i );
+          const float4 ex = ldStream( a.extent + i );
+          tidx = __float_as_uint( lo.w );
+          float4 const *m = a.mats + 4ull * tidx;
+          const float4 m0 = __ldg( m + 0 );
+          const float4 m1 = __ldg( m + 1 );
+          const float4 m2 = __ldg( m + 2 );
+          const float4 m3 = __ldg( m + 3 );
+          obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+        }
+#if DPCU_MV_PREFETCH
+        {
+          // step w + DIST of this line: object runs always; matrices when this step's indices are consecutive
+          // (then the next steps' very likely continue the run; a wrong guess costs one useless L2 fill)
+          const uint32_t wp = w + DPCU_MV_PREFETCH_DIST;
+          const uint32_t ip = ( ( word0 + wp ) << 5 );
+          const uint32_t t0 = __shfl_sync( 0xffffffffu, tidx, 0 );
+          const bool     run = __all_sync( 0xffffffffu, tidx == t0 + lane );
+          if ( wp < steps && ip + 32u <= a.n )
+          {
+#if DPCU_MV_PREFETCH == 2
+            if ( lane == 0 )
+            {
+              bulkPrefetchL2( a.lowerIdx + ip, 512u );
+              bulkPrefetchL2( a.extent + ip, 512u );
+              if ( run && t0 + 32u * DPCU_MV_PREFETCH_DIST + 32u <= a.nMats )
+                bulkPrefetchL2( a.mats + 4ull * ( t0 + 32u * DPCU_MV_PREFETCH_DIST ), 2048u );
+            }
+#else
+            if ( lane < 8u ) prefetchL2( ( ( lane & 1u ) ? a.extent : a.lowerIdx ) + ip + ( lane >> 1 ) * 8u );
+            else if ( lane < 24u && run && t0 + 32u * DPCU_MV_PREFETCH_DIST + 32u <= a.nMats )
+              prefetchL2( a.mats + 4ull * ( t0 + 32u * DPCU_MV_PREFETCH_DIST ) + ( lane - 8u ) * 8u );
+#endif
+          }
+        }
+#endif
+        const ObbBall ball = makeBall( obb, a.filterHalf );
+        uint32_t mySlot = 0xffffffffu;
+#pragma unroll
+        for ( int p = 0; p < kPairs; ++p )
+        {
+          bool vis[2], inv[2];
+          classifyPair( ball, a.pairFilter[p], vis, inv );
+#pragma unroll
+          for ( int e = 0; e < 2; ++e )
+          {
+            const int v = 2 * p + e;
+            if ( v >= NV ) break;
+            const uint32_t bv = __ballot_sync( 0xffffffffu, vis[e] ) & liveMask;
+            const bool     open = !vis[e] && !inv[e];
+            const uint32_t bo = __ballot_sync( 0xffffffffu, open ) & liveMask;
+            if ( lane == 0 ) sh.acc[v][w] = bv;
+            if ( bo )
+            {
+              // queue the undecided pairs of this view: the object's OBB once (first view that needs it), a tag per pair
+              const bool     mine  = ( bo >> lane ) & 1u;
+              const bool     fresh = mine && mySlot == 0xffffffffu;
+              const uint32_t bf    = __ballot_sync( 0xffffffffu, fresh );
+              if ( fresh )
+              {
+                mySlot = nObj + __popc( bf & below );
+                sh.obb[0][mySlot] = obb.pt; sh.obb[1][mySlot] = obb.ax; sh.obb[2][mySlot] = obb.ay; sh.obb[3][mySlot] = obb.az;
+                sh.pos[mySlot] = uint16_t( ( w << 5 ) | lane );
+              }
+              nObj += __popc( bf );
+              if ( mine ) sh.tag[nPairs + __popc( bo & below )] = uint16_t( ( mySlot << 3 ) | uint32_t( v ) );
+              nPairs += __popc( bo );
+            }
+          }
+        }
+        if ( nPairs >= kMvFlushAt || nObj > kMvObjCap - 32u )
+        {
+          mvFlush<NV>( sh, sP, a.onePair, nPairs, lane );
+          nObj = nPairs = 0;
+        }
+      }
+      // end of the line: previous words (their latency hides behind the last exact pass), then the finished words
+      uint32_t old[NV];
+#pragma unroll
+      for ( int v = 0; v < NV; ++v ) old[v] = wordLive ? __ldcg( a.out[v].bits + myWord ) : 0u;
+      if ( nPairs ) mvFlush<NV>( sh, sP, a.onePair, nPairs, lane );
+      else __syncwarp();
+#pragma unroll
+      for ( int v = 0; v < NV; ++v )
+      {
+        ViewOut const &o = a.out[v];
+        uint32_t flips = 0;
+        if ( wordLive )
+        {
+          const uint32_t acc = sh.acc[v][lane];
+          o.bits[myWord] = acc;
+          if ( o.mirror ) o.mirror[myWord] = acc;              // the same line over PCIe into pinned host memory
+          for ( uint32_t p = 0; p < a.nPeers; ++p )
+          {
+            if ( o.peer[p] ) o.peer[p][a.peerWordOffset + myWord] = acc;
+          }
+          if ( a.buildChanged )
+          {
+            const uint32_t c = old[v] ^ acc;
+            o.chg[myWord] = c;
+            flips = __popc( c );
+          }
+        }
+        if ( a.buildChanged )
+        {
+#pragma unroll
+          for ( int d = 16; d > 0; d >>= 1 ) flips += __shfl_xor_sync( 0xffffffffu, flips, d );
+          if ( kFuseList )
+          {
+            // publish this line's count right away; its place in the list is resolved one line later (below)
+            if ( lane == 0 ) lookStore( o.look + line, lookPack( o.epoch, line == 0 ? kLookPrefix : kLookAggregate, flips ) );
+          }
+          else if ( lane == 0 && flips ) atomicAdd( o.seg + ( word0 >> ( kSegObjectsLog2 - 5 ) ), flips );
+        }
+      }
+      __syncwarp();                                          // acc[][] is rewritten by the next line's first step
+      if ( kFuseList && a.buildChanged )
+      {
+        if ( pending != kNoLine ) resolveLine<NV>( a, pending, nLines, nWords, lane );
+        pending = line;
+      }
+      if ( !kFuseList ) line += nWarps;
+    }
+    if ( kFuseList && a.buildChanged && pending != kNoLine ) resolveLine<NV>( a, pending, nLines, nWords, lane );
+    if ( kFuseList ) rearmInLastCta( a.done );
+    else if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+  }
+}

@@ -207,7 +207,8 @@ def test_multi_view_equals_single_views(capi, port):
 # ------------------------------------------------------------------ both exact kernel forms, 1..8 views
 # every exact form of K2: DPCU_KERNEL_* plus, for the line-granular kernel, how the changed list is built
 # (inside the kernel by single-pass look-back, the default, or by segment counters + the compaction kernel)
-KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4, "lines_w8": 4}
+KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4, "lines_w8": 4,
+           "lines_pairs": 7, "lines_pairs_compact": 7}
 
 
 def _select_kernel(capi, ctx, kernel):
@@ -584,7 +585,7 @@ def test_peer_bitset_gather_in_kernel_epilogue(capi, port, nv):
 
 
 # ------------------------------------------------------------------ the multi-view filter (cull_filter.cuh)
-@pytest.mark.parametrize("kernel", ["auto", "views", "lines"])
+@pytest.mark.parametrize("kernel", ["auto", "views", "lines", "lines_pairs"])
 @pytest.mark.parametrize("seed", [101, 102, 103])
 def test_filter_decisions_on_the_boundaries(capi, port, golden, kernel, seed):
     """The filter may only decide what it can prove.  A scene where a large share of the (object, view) pairs
@@ -618,7 +619,8 @@ def test_filter_decisions_on_the_boundaries(capi, port, golden, kernel, seed):
             ctx.close()
 
 
-def test_filter_random_scales_fuzz(capi, port):
+@pytest.mark.parametrize("kernel", ["auto", "lines_pairs"])
+def test_filter_random_scales_fuzz(capi, port, kernel):
     """Affine objects over 60 orders of magnitude against random perspective / orthographic views: whatever the
     filter decides must be what the reference arithmetic decides."""
     for seed in range(5):
@@ -638,6 +640,7 @@ def test_filter_random_scales_fuzz(capi, port):
             views.append(scenes.mat_mul(view, proj))
         vps = np.ascontiguousarray(np.stack(views), np.float32)
         ctx = capi.Cull(0)
+        _select_kernel(capi, ctx, kernel)
         ctx.set_objects(lower4, extent4, tidx)
         ctx.set_matrices(mats.reshape(-1))
         res = [ctx.result_create() for _ in range(6)]
@@ -668,7 +671,8 @@ class _Mirror:
             b.close()
 
 
-@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact", "lines_w8"])
+@pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact", "lines_w8", "lines_pairs",
+                                    "lines_pairs_compact"])
 @pytest.mark.parametrize("nv", [1, 3])
 def test_host_mirror_matches_port(capi, port, kernel, nv):
     """dpcuCullResultSetHostMirror: after run + synchronize the pinned buffers hold exactly what
