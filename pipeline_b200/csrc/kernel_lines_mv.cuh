@@ -25,8 +25,17 @@ namespace dpcu
 #ifndef DPCU_MV_MIN_CTAS
 #define DPCU_MV_MIN_CTAS 4
 #endif
+#ifndef DPCU_MV_PIPE
+#define DPCU_MV_PIPE 1              // 0: loads as they come, 1: transform index a step ahead, 2: 1 + L2 prefetch of the next
+#endif                              // step's matrix, 3: all six loads a step ahead (register double buffer)
+#ifndef DPCU_MV_CLAMP
+#define DPCU_MV_CLAMP 1             // lanes past the end re-read the last object instead of branching around the loads
+#endif
+#ifndef DPCU_MV_APPEND
+#define DPCU_MV_APPEND 1            // 0: undecided pairs queued view by view (a branch per view), 1: one branch per step
+#endif
 #ifndef DPCU_MV_PREFETCH
-#define DPCU_MV_PREFETCH 2          // 0: none, 1: per-lane prefetch.global.L2, 2: bulk L2 prefetch by one lane (TMA unit)
+#define DPCU_MV_PREFETCH 0          // 0: none, 1: per-lane prefetch.global.L2, 2: bulk L2 prefetch by one lane (TMA unit)
 #endif
 #ifndef DPCU_MV_PREFETCH_DIST
 #define DPCU_MV_PREFETCH_DIST 2     // steps ahead
@@ -116,6 +125,32 @@ namespace dpcu
 #endif
       }
 #endif
+#if DPCU_MV_PIPE >= 1
+      // The transform index of the NEXT step is fetched a step ahead (one register), so a step's six 16-byte loads
+      // go out together: one DRAM round trip per step instead of two dependent ones (object -> its matrix), which
+      // were 40 % of all stall samples of this kernel (profiles/r02_mv6_nopipe_*).
+      uint32_t idxNext = 0;
+      {
+        const uint32_t i0 = min( ( word0 << 5 ) + lane, a.n - 1u );
+        idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i0 ) + 3 );
+      }
+#endif
+#if DPCU_MV_PIPE == 3
+      // ... and the loads themselves run one step ahead of the arithmetic (register double buffer)
+      uint32_t idxNext2 = 0;
+      float4 nLo, nEx, nM0, nM1, nM2, nM3;
+      nLo = nEx = nM0 = nM1 = nM2 = nM3 = make_float4( 0.f, 0.f, 0.f, 0.f );
+      {
+        const uint32_t i0 = ( word0 << 5 ) + lane, i1 = i0 + 32u;
+        if ( steps > 1 && i1 < a.n ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
+        if ( i0 < a.n )
+        {
+          float4 const *m = a.mats + 4ull * idxNext;
+          nLo = ldStream( a.lowerIdx + i0 ); nEx = ldStream( a.extent + i0 );
+          nM0 = __ldg( m + 0 ); nM1 = __ldg( m + 1 ); nM2 = __ldg( m + 2 ); nM3 = __ldg( m + 3 );
+        }
+      }
+#endif
 #pragma unroll 1
       for ( uint32_t w = 0; w < steps; ++w )
       {
@@ -123,20 +158,57 @@ namespace dpcu
         const bool     live = i < a.n;
         const uint32_t liveMask = __ballot_sync( 0xffffffffu, live );
         Obb obb;
+#if DPCU_MV_PIPE == 3 || !DPCU_MV_CLAMP
         obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );   // not affine: never decided, masked by liveMask
+#endif
         uint32_t tidx = 0;
+#if DPCU_MV_PIPE == 3
+        {
+          const float4 lo = nLo, ex = nEx, m0 = nM0, m1 = nM1, m2 = nM2, m3 = nM3;
+          tidx = idxNext;
+          const uint32_t i1 = i + 32u, i2 = i + 64u;
+          idxNext = idxNext2;
+          if ( w + 1 < steps && i1 < a.n )
+          {
+            float4 const *m = a.mats + 4ull * idxNext;
+            nLo = ldStream( a.lowerIdx + i1 ); nEx = ldStream( a.extent + i1 );
+            nM0 = __ldg( m + 0 ); nM1 = __ldg( m + 1 ); nM2 = __ldg( m + 2 ); nM3 = __ldg( m + 3 );
+          }
+          if ( w + 2 < steps && i2 < a.n ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i2 ) + 3 );
+          if ( live ) obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+        }
+#else
+#if DPCU_MV_CLAMP
+        // lanes past the end re-read the last object (no branch, no zero fill); liveMask drops their results
+        const uint32_t ic = min( i, a.n - 1u );
+        {
+#else
+        const uint32_t ic = i;
         if ( live )
         {
-          const float4 lo = ldStream( a.lowerIdx + i );
-          const float4 ex = ldStream( a.extent + i );
+#endif
+#if DPCU_MV_PIPE >= 1
+          tidx = idxNext;
+#endif
+          const float4 lo = ldStream( a.lowerIdx + ic );
+          const float4 ex = ldStream( a.extent + ic );
+#if DPCU_MV_PIPE == 0
           tidx = __float_as_uint( lo.w );
+#endif
           float4 const *m = a.mats + 4ull * tidx;
           const float4 m0 = __ldg( m + 0 );
           const float4 m1 = __ldg( m + 1 );
           const float4 m2 = __ldg( m + 2 );
           const float4 m3 = __ldg( m + 3 );
+#if DPCU_MV_PIPE >= 1
+          {
+            const uint32_t i1 = min( i + 32u, a.n - 1u );
+            if ( w + 1 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
+          }
+#endif
           obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
         }
+#endif
 #if DPCU_MV_PREFETCH
         {
           // step w + DIST of this line: object runs always; matrices when this step's indices are consecutive
@@ -164,6 +236,7 @@ namespace dpcu
         }
 #endif
         const ObbBall ball = makeBall( obb, a.filterHalf );
+#if DPCU_MV_APPEND == 0
         uint32_t mySlot = 0xffffffffu;
 #pragma unroll
         for ( int p = 0; p < kPairs; ++p )
@@ -197,6 +270,59 @@ namespace dpcu
             }
           }
         }
+#else
+        // All views in one straight-line block (the three pair classifications interleave freely), each lane
+        // collecting its object's undecided views as a bit mask; ONE branch per step then queues them.
+        uint32_t openMask = 0;
+#pragma unroll
+        for ( int p = 0; p < kPairs; ++p )
+        {
+          bool vis[2], inv[2];
+          classifyPair( ball, a.pairFilter[p], vis, inv );
+#pragma unroll
+          for ( int e = 0; e < 2; ++e )
+          {
+            const int v = 2 * p + e;
+            if ( v >= NV ) break;
+            const uint32_t bv = __ballot_sync( 0xffffffffu, vis[e] ) & liveMask;
+            if ( lane == 0 ) sh.acc[v][w] = bv;
+            if ( !vis[e] && !inv[e] ) openMask |= 1u << v;
+          }
+        }
+        if ( !live ) openMask = 0;
+        if ( __any_sync( 0xffffffffu, openMask != 0 ) )
+        {
+          // object slots by ballot; tag slots by an exclusive prefix of the per-lane counts, one ballot per count bit
+          const uint32_t cnt = __popc( openMask );
+          const uint32_t bh  = __ballot_sync( 0xffffffffu, openMask != 0 );
+          uint32_t pre = 0, tot = 0;
+          constexpr int kCountBits = NV >= 8 ? 4 : ( NV >= 4 ? 3 : 2 );
+#pragma unroll
+          for ( int bit = 0; bit < kCountBits; ++bit )
+          {
+            const uint32_t bb = __ballot_sync( 0xffffffffu, ( cnt >> bit ) & 1u );
+            pre += __popc( bb & below ) << bit;
+            tot += __popc( bb ) << bit;
+          }
+          if ( openMask )
+          {
+            const uint32_t slot = nObj + __popc( bh & below );
+            sh.obb[0][slot] = obb.pt; sh.obb[1][slot] = obb.ax; sh.obb[2][slot] = obb.ay; sh.obb[3][slot] = obb.az;
+            sh.pos[slot] = uint16_t( ( w << 5 ) | lane );
+            uint32_t t = nPairs + pre, m = openMask;
+            do
+            {
+              sh.tag[t++] = uint16_t( ( slot << 3 ) | uint32_t( __ffs( m ) - 1 ) );
+              m &= m - 1u;
+            } while ( m );
+          }
+          nObj   += __popc( bh );
+          nPairs += tot;
+        }
+#endif
+#if DPCU_MV_PIPE == 2
+        if ( w + 1 < steps && i + 32u < a.n ) prefetchL2( a.mats + 4ull * idxNext );
+#endif
         if ( nPairs >= kMvFlushAt || nObj > kMvObjCap - 32u )
         {
           mvFlush<NV>( sh, sP, a.onePair, nPairs, lane );
