@@ -79,6 +79,8 @@ int dpcuBufferDevicePointer(const dpcuBuffer *buffer, void **devicePointer);
 int dpcuBufferUpload(dpcuBuffer *buffer, size_t offset, const void *host, size_t bytes, dpcuStream *stream);
 int dpcuBufferDownload(const dpcuBuffer *buffer, size_t offset, void *host, size_t bytes, dpcuStream *stream);
 int dpcuBufferFill(dpcuBuffer *buffer, int byteValue, size_t bytes, size_t offset);
+/* the same, ordered on `stream` (cudaMemsetAsync) */
+int dpcuBufferFillAsync(dpcuBuffer *buffer, int byteValue, size_t bytes, size_t offset, dpcuStream *stream);
 
 /* dp::cuda::BufferHost::create (pinned, optionally mapped/portable; dp/cuda/src/BufferHost.cpp) */
 #define DPCU_HOST_DEFAULT   0u
@@ -118,6 +120,7 @@ int dpcuEventElapsedMs(dpcuEvent *start, dpcuEvent *stop, float *milliseconds);
  * objects whose visibility changed in the last cull. */
 typedef struct dpcuCull       dpcuCull;
 typedef struct dpcuCullResult dpcuCullResult;
+typedef struct dpcuTree       dpcuTree;        /* transform layer, below */
 
 /* replaces cpu::Manager::create + groupCreate (dp/culling/cpu/src/ManagerImpl.cpp:171-189) */
 int dpcuCullCreate(dpcuCull **out, int device);
@@ -145,10 +148,20 @@ int dpcuCullSetMatrices(dpcuCull *ctx, const void *matrices, size_t count, size_
  * ignored like markMatrixDirty does.  memspace describes `matrices`; `indices` is host memory. */
 int dpcuCullUpdateMatrices(dpcuCull *ctx, const uint32_t *indices, size_t n, const void *matrices,
                            size_t strideBytes, int memspace);
-/* Zero-copy feed: cull straight out of a device matrix array owned by someone else, e.g. the
- * world matrices of a dpcuTree (SURVEY.md section 7 hard part 4).  64-byte stride.  The memory
- * must stay valid until the context is rebound, given its own copy, or destroyed. */
+/* Zero-copy feed: cull straight out of a device matrix array owned by someone else (SURVEY.md
+ * section 7 hard part 4).  64-byte stride.  The memory must stay valid until the context is
+ * rebound, given its own copy, or destroyed.  ORDERING IS THE CALLER'S: whatever writes these
+ * matrices must be ordered before every dpcuCullRun that reads them, and after the previous one,
+ * by running on the same stream or through events (dpcuStreamWaitEvent).  For the world matrices
+ * of a dpcuTree use dpcuCullBindTree, which does that ordering itself. */
 int dpcuCullBindMatrices(dpcuCull *ctx, const void *deviceMatrices, size_t count);
+/* Zero-copy feed out of a dpcuTree's world matrices (xbar: TransformTree -> culling,
+ * dp/sg/xbar/culling/src/CullingImpl.cpp:126-144 without the host round trip).  Every dpcuCullRun
+ * waits for the tree's last dpcuTreeCompute and every dpcuTreeCompute waits for the last cull that
+ * read the matrices, on whatever streams they run (events, no host block); the binding follows the
+ * tree when dpcuTreeSetTopology reallocates its arrays.  Unbind (dpcuCullBindMatrices /
+ * dpcuCullSetMatrices / another tree) or destroy the context before destroying the tree. */
+int dpcuCullBindTree(dpcuCull *ctx, dpcuTree *tree);
 int dpcuCullGetMatrixCount(const dpcuCull *ctx, size_t *count);
 
 /* groupCreateResult (dp/culling/cpu/src/ManagerImpl.cpp:191-194) */
@@ -230,6 +243,9 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 #define DPCU_KERNEL_LINES_PAIRS  7      /* >= 2 views: line-granular, two views per packed filter instruction, */
                                         /* undecided pairs queued across the line's steps, L2 bulk prefetch;   */
                                         /* what AUTO and peer bitsets use for several views (1 view: = LINES)  */
+#define DPCU_KERNEL_GRID         8      /* one thread per object on a co-resident (cooperative) grid, the ordered */
+                                        /* changed list behind one grid-wide barrier: one launch per cull for     */
+                                        /* small groups (option; measured slower than direct + compaction)        */
 #define DPCU_CULL_OPT_FMA           2   /* 1 = fused multiply-add fast mode: NOT bit-exact, reporting only   */
 #define DPCU_CULL_OPT_CHANGED_LIST  3   /* 1 (default) = build the ordered changed list, 0 = bits only       */
 #define DPCU_CULL_OPT_CTAS_PER_SM   4   /* 0 = auto                                                          */
@@ -287,7 +303,6 @@ int dpcuDeviceEnablePeerAccess(int device, int peer);
  * resident in HBM, level-sorted {parent, transform} lists, dirty bit arrays; compute()
  * propagates world = local * world[parent] level by level for dirty nodes
  * (dp/transform/src/Tree.cpp:133-166). */
-typedef struct dpcuTree dpcuTree;
 int dpcuTreeCreate(dpcuTree **out, int device);
 int dpcuTreeDestroy(dpcuTree *tree);
 /* Topology as Tree keeps it (Tree.h:113-128): entries = {parent, transform} u32 pairs of all
@@ -335,6 +350,9 @@ int dpcuCullRunWithTree(dpcuCull *ctx, dpcuTree *tree, dpcuCullResult *const *re
  * [first, first+count).  Bit-identical to the host generator (tests/test_scene_gen.py). */
 int dpcuSceneGenerate(uint64_t seed, uint64_t first, size_t count, uint32_t indexBase,
                       float *lower4Device, float *extent4Device, float *matricesDevice, dpcuStream *stream);
+/* Bench support: stream `bytes` of device memory through L2 once (reads only).  bench.py runs it after its
+ * L2-flushing write so that the L2 is cold and CLEAN when a timed step of a small workload starts. */
+int dpcuDebugReadSweep(const void *deviceMemory, size_t bytes, dpcuStream *stream);
 
 #ifdef __cplusplus
 }

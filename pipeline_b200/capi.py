@@ -21,8 +21,8 @@ MEM_HOST, MEM_DEVICE = 0, 1
 OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF, OPT_FUSE_LIST, OPT_LAST_KERNEL, OPT_FILTER, OPT_LINE_WORDS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 TREE_OPT_WIDE_MIN_NODES = 1
 KERNEL_NAMES = {1: "cullDirectKernel", 2: "cullStagedKernel", 3: "cullViewsKernel", 4: "cullLinesKernel", 5: "cullViewsKernel", 6: "cullFusedLeafKernel",
-                7: "cullLinesMvKernel"}
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS, KERNEL_FUSED_LEAF, KERNEL_LINES_PAIRS = 0, 1, 2, 3, 4, 5, 6, 7
+                7: "cullLinesMvKernel", 8: "cullGridKernel"}
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED, KERNEL_VIEWS, KERNEL_LINES, KERNEL_VIEWS_CHAINS, KERNEL_FUSED_LEAF, KERNEL_LINES_PAIRS, KERNEL_GRID = 0, 1, 2, 3, 4, 5, 6, 7, 8
 MAX_VIEWS = 8
 
 _vp = C.c_void_p
@@ -97,6 +97,7 @@ def _declare(L):
         "dpcuBufferUpload": [_vp, C.c_size_t, _vp, C.c_size_t, _vp],
         "dpcuBufferDownload": [_vp, C.c_size_t, _vp, C.c_size_t, _vp],
         "dpcuBufferFill": [_vp, C.c_int, C.c_size_t, C.c_size_t],
+        "dpcuBufferFillAsync": [_vp, C.c_int, C.c_size_t, C.c_size_t, _vp],
         "dpcuHostBufferCreate": [C.POINTER(_vp), C.c_size_t, C.c_uint],
         "dpcuHostBufferDestroy": [_vp],
         "dpcuHostBufferPointer": [_vp, C.POINTER(_vp)],
@@ -121,6 +122,7 @@ def _declare(L):
         "dpcuCullSetMatrices": [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int],
         "dpcuCullUpdateMatrices": [_vp, _u32p, C.c_size_t, _vp, C.c_size_t, C.c_int],
         "dpcuCullBindMatrices": [_vp, _vp, C.c_size_t],
+        "dpcuCullBindTree": [_vp, _vp],
         "dpcuCullGetMatrixCount": [_vp, _szp],
         "dpcuCullResultCreate": [_vp, C.POINTER(_vp)],
         "dpcuCullResultDestroy": [_vp],
@@ -162,6 +164,7 @@ def _declare(L):
         "dpcuTreeGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
         "dpcuTreeSetOption": [_vp, C.c_int, C.c_size_t],
         "dpcuSceneGenerate": [C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32, _vp, _vp, _vp, _vp],
+        "dpcuDebugReadSweep": [_vp, C.c_size_t, _vp],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -227,8 +230,12 @@ class Buffer:
         check(lib().dpcuBufferDownload(self.h, offset, _ptr(arr), arr.nbytes, stream.h if stream else None))
         return arr
 
-    def fill(self, byte, nbytes=None, offset=0):
-        check(lib().dpcuBufferFill(self.h, byte, self.nbytes if nbytes is None else nbytes, offset))
+    def fill(self, byte, stream=None, nbytes=None, offset=0):
+        n = self.nbytes if nbytes is None else nbytes
+        if stream is not None:
+            check(lib().dpcuBufferFillAsync(self.h, byte, n, offset, stream.h))
+        else:
+            check(lib().dpcuBufferFill(self.h, byte, n, offset))
 
     def close(self):
         if self.h:
@@ -471,6 +478,10 @@ class Cull:
     def bind_matrices(self, device_ptr, count):
         check(lib().dpcuCullBindMatrices(self.h, device_ptr, count))
 
+    def bind_tree(self, tree):
+        """cull out of the tree's world matrices in place; culls and tree computes are ordered by events"""
+        check(lib().dpcuCullBindTree(self.h, tree.h))
+
     def matrix_count(self):
         c = C.c_size_t()
         check(lib().dpcuCullGetMatrixCount(self.h, C.byref(c)))
@@ -638,3 +649,8 @@ def enable_peer_access(device, peer):
 def scene_generate(seed, first, count, index_base, lower_ptr, extent_ptr, mats_ptr, stream=None):
     check(lib().dpcuSceneGenerate(seed, first, count, index_base, lower_ptr, extent_ptr, mats_ptr,
                                   stream.h if stream else None))
+
+
+def read_sweep(device_ptr, nbytes, stream=None):
+    """bench support: read a device buffer once (leaves the L2 cold and clean after a flush write)"""
+    check(lib().dpcuDebugReadSweep(device_ptr, nbytes, stream.h if stream else None))

@@ -45,6 +45,7 @@
 #include "kernel_staged.cuh"
 #include "kernel_lines.cuh"
 #include "kernel_lines_mv.cuh"
+#include "kernel_grid.cuh"
 #include "kernel_fused_leaf.cuh"
 #include "kernel_misc.cuh"
 #endif   // !DPCU_FMA_VARIANT
@@ -96,6 +97,7 @@ struct dpcuCullResult
   dpcuCullResult *next = nullptr, *prev = nullptr;
 
   dpcu::DeviceArray look;                           // look-back entries of the fused list, one per 1024 objects
+  dpcu::DeviceArray gridTotals;                     // cullGridKernel: flips per CTA
   size_t   lookCap = 0;
   uint32_t lookEpoch = 0;
   dpcu::DeviceArray visible, visCounters;           // dpcuCullResultBuildVisibleList: indices | done[4], seg[cap], prefix[cap]
@@ -122,6 +124,7 @@ struct dpcuCull
   dpcu::StreamFence uploads;     // object / matrix updates submitted on `stream`
   dpcu::StreamFence lastRun;     // last cull submitted (possibly on a caller stream); updates are ordered after it
   float const *boundMats = nullptr;      // borrowed device matrices (dpcuCullBindMatrices)
+  dpcuTree    *boundTree = nullptr;      // ... of this tree (dpcuCullBindTree / dpcuCullRunWithTree): culls and its computes are ordered by events
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
@@ -194,6 +197,7 @@ namespace dpcu
       r->lookCap = r->look.capacity / 8;
       r->lookEpoch = 0;
     }
+    if ( ctx->optChanged && !r->gridTotals.ptr ) DPCU_TRY( r->gridTotals.reserve( ( size_t( ctx->smCount ) * 32 + 64 ) * 4, false, stream ) );
     if ( nSegs + 1 > r->nSegsCap )
     {
       size_t cap = nSegs + 1 + nSegs / 2;
@@ -231,7 +235,13 @@ namespace dpcu
     }
     double q = 0.0;
     for ( int r = 0; r < 4; ++r ) q += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
-    f.q = roundUp( marginScale * q / 131072.0 );
+    // q = +inf switches the filter off for this view (classify: `sane` is false): a non-finite entry, or a sum so small
+    // that the relative margin would not cover the ABSOLUTE error of underflowing products (each up to 2^-150; with the
+    // sum >= 2^-100 the margin is >= 2^-117), or so large that the margin arithmetic could overflow
+    bool finite = true;
+    for ( int k = 0; k < 16; ++k ) finite = finite && std::isfinite( vp[k] );
+    const bool usable = finite && q >= 7.888609052210118e-31 /* 2^-100 */ && q <= 549755813888.0 /* 2^39 */;
+    f.q = usable ? roundUp( marginScale * q / 131072.0 ) : INFINITY;
     f.pad = 0.0f;
     memcpy( f.rows, vp, 64 );
   }
@@ -299,6 +309,7 @@ namespace dpcu
       args.out[v].seg   = r->segPtr();
       args.out[v].prefix = r->prefixPtr();
       args.out[v].mirror = r->dBits;
+      args.out[v].gridTotals = static_cast<uint32_t *>( r->gridTotals.ptr );
       for ( int p = 0; p < kMaxPeers; ++p ) args.out[v].peer[p] = p < r->nPeers ? r->peer[p] : nullptr;
       if ( uint32_t( r->nPeers ) > args.nPeers ) args.nPeers = uint32_t( r->nPeers );
       args.peerWordOffset = uint32_t( r->peerWordOffset );
@@ -342,12 +353,19 @@ namespace dpcu
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
     args.lineWords = ctx->optLineWords ? uint32_t( ctx->optLineWords ) : 32u;
-    const bool useLines  = !ctx->optFma && ( peers || ctx->optKernel == DPCU_KERNEL_LINES || ctx->optKernel == DPCU_KERNEL_LINES_PAIRS || autoLines );
+    const bool useLines  = !ctx->optFma && ( ( peers && !leaf ) || ctx->optKernel == DPCU_KERNEL_LINES || ctx->optKernel == DPCU_KERNEL_LINES_PAIRS || autoLines );
     // several views: the pair-filter form with the queued exact passes (kernel_lines_mv.cuh), unless the earlier form is asked for
     const bool useLinesMv = useLines && !leaf && NV >= 2 && ctx->optKernel != DPCU_KERNEL_LINES;
     if ( useLinesMv ) args.lineWords = 32u;
-    *mirrorsWritten = useLines && !leaf;
-    const bool fuseList = useLines && !leaf && ctx->optChanged && ctx->optFuseList;
+    // One thread per object on a co-resident grid with one grid-wide barrier between the cull and the list
+    // (kernel_grid.cuh): one launch per cull for small groups.  Built for BASELINE config C2 and measured there against
+    // direct + compaction (device time of the step, L2 flushed and swept clean): 37.8 us vs 36.0 us at 1 Mi objects, 83 vs
+    // 53 us at 2 Mi - the barrier makes every CTA wait for the slowest one and phase 2 starts cold, which costs more than
+    // the second launch it saves (that launch now overlaps the cull kernel's tail, see the compaction launch below).
+    // So AUTO does not pick it; DPCU_KERNEL_GRID does.
+    const bool useGrid = !useLines && !leaf && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_GRID;
+    *mirrorsWritten = ( useLines || useGrid ) && !leaf;
+    const bool fuseList = ( ( useLines && ctx->optFuseList ) || useGrid ) && !leaf && ctx->optChanged;
     *listBuilt = fuseList;
     if ( fuseList )
     {
@@ -367,12 +385,12 @@ namespace dpcu
         args.out[v].hostCap     = uint32_t( r->hChangedCap < 0xffffffffull ? r->hChangedCap : 0xffffffffull );
       }
     }
-    if ( peers && ( ctx->optFma || leaf ) )
-      return fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: peer bitsets are served by the line-granular kernel only (not the FMA or fused-leaf forms)" );
+    if ( peers && ctx->optFma )
+      return fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: peer bitsets are not served by the FMA reporting mode" );
     const bool useFused  = leaf != nullptr;
-    const bool useStaged = !useFused && !useLines && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
+    const bool useStaged = !useFused && !useLines && !useGrid && !ctx->optFma && ctx->optKernel == DPCU_KERNEL_STAGED;
     const bool useChains = ctx->optKernel == DPCU_KERNEL_VIEWS_CHAINS;
-    const bool useViews  = !useFused && !useLines && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || useChains || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
+    const bool useViews  = !useFused && !useLines && !useGrid && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || useChains || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
     // the last CTA's scan re-arms ticket and chunk counter; without a changed list nobody does
     if ( useStaged && !ctx->optChanged ) DPCU_CUDA( cudaMemsetAsync( results[0]->donePtr(), 0, 16, stream ) );
@@ -394,6 +412,7 @@ namespace dpcu
       else if ( useLinesMv ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, false>, kCullThreads, 0 );
       else if ( useLines && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, true>, kCullThreads, 0 );
       else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, false>, kCullThreads, 0 );
+      else if ( useGrid ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullGridKernel<NV>, kCullThreads, 0 );
       else if ( ctx->optFma ) perSm = occupancyCullDirectFma<NV>();
       else if ( useStaged ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullStagedKernel<NV>, kCullThreads, stagedSmem );
       else if ( useViews && useChains ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV, false>, kCullThreads, 0 );
@@ -440,6 +459,18 @@ namespace dpcu
       else                          cullLinesKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
     }
+    else if ( useGrid )
+    {
+      // cooperative launch: the grid-wide barrier needs every CTA resident, and the runtime checks that it is
+      if ( ctx->optCtasPerSm > 0 )
+      {
+        int fit = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor( &fit, cullGridKernel<NV>, kCullThreads, 0 );
+        if ( grid > ctx->smCount * fit ) grid = ctx->smCount * ( fit > 0 ? fit : 1 );
+      }
+      void *params[] = { &args };
+      DPCU_CUDA( cudaLaunchCooperativeKernel( reinterpret_cast<void const *>( &cullGridKernel<NV> ), dim3( unsigned( grid ) ), dim3( kCullThreads ), params, 0, stream ) );
+    }
     else if ( ctx->optFma )
     {
       DPCU_CUDA( launchCullDirectFma<NV>( args, grid, stream ) );
@@ -462,7 +493,7 @@ namespace dpcu
     }
     if ( evStop ) DPCU_CUDA( cudaEventRecord( evStop, stream ) );
     ++ctx->launches;
-    ctx->lastKernel = useFused ? DPCU_KERNEL_FUSED_LEAF : useLinesMv ? DPCU_KERNEL_LINES_PAIRS : useLines ? DPCU_KERNEL_LINES : ctx->optFma ? DPCU_KERNEL_DIRECT
+    ctx->lastKernel = useFused ? DPCU_KERNEL_FUSED_LEAF : useLinesMv ? DPCU_KERNEL_LINES_PAIRS : useLines ? DPCU_KERNEL_LINES : useGrid ? DPCU_KERNEL_GRID : ctx->optFma ? DPCU_KERNEL_DIRECT
                     : useStaged ? DPCU_KERNEL_STAGED : useViews ? ( useChains ? DPCU_KERNEL_VIEWS_CHAINS : DPCU_KERNEL_VIEWS ) : DPCU_KERNEL_DIRECT;
     return DPCU_OK;
   }
@@ -587,6 +618,7 @@ extern "C"
     DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
     DPCU_TRY( ctx->mats.reserve( ( count ? count : 1 ) * 64, false, ctx->stream ) );
     ctx->boundMats = nullptr;
+    ctx->boundTree = nullptr;
     ctx->nMats = count;
     if ( !count ) return DPCU_OK;
     if ( strideBytes == 64 ) return dpcu::uploadOrCopy( ctx->mats.ptr, matrices, count * 64, memspace, ctx );
@@ -650,7 +682,18 @@ extern "C"
     DPCU_REQUIRE( ( reinterpret_cast<uintptr_t>( deviceMatrices ) & 15 ) == 0, "matrices must be 16-byte aligned" );
     DPCU_REQUIRE( count < ( size_t( 1 ) << 32 ), "matrix count must fit 32 bits" );
     ctx->boundMats = static_cast<float const *>( deviceMatrices );
+    ctx->boundTree = nullptr;
     ctx->nMats = count;
+    return DPCU_OK;
+  }
+
+  int dpcuCullBindTree( dpcuCull *ctx, dpcuTree *tree )
+  {
+    DPCU_REQUIRE( ctx && tree, "NULL argument" );
+    DPCU_REQUIRE( tree->device == ctx->device, "tree and culling context live on different devices" );
+    ctx->boundTree = tree;
+    ctx->boundMats = static_cast<float const *>( tree->world.ptr );
+    ctx->nMats     = tree->numNodes;
     return DPCU_OK;
   }
 
@@ -683,7 +726,7 @@ extern "C"
     r->done.hostWait();
     r->done.destroy();
     r->bits.release(); r->chg.release(); r->changed.release(); r->counters.release();
-    r->visible.release(); r->visCounters.release(); r->look.release();
+    r->visible.release(); r->visCounters.release(); r->look.release(); r->gridTotals.release();
     if ( r->prev ) r->prev->next = r->next; else ctx->results = r->next;
     if ( r->next ) r->next->prev = r->prev;
     delete r;
@@ -692,7 +735,9 @@ extern "C"
 
 }   // extern "C"
 
-  static int runCull( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, cudaStream_t s, dpcu::LeafArgs const *leaf )
+  // Everything of a cull that can fail before a kernel is launched: arguments, index range, host mirror sizes, peer
+  // configuration, result capacity.  dpcuCullRunWithTree runs it BEFORE it touches the tree's dirty state.
+  static int prepareCull( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, cudaStream_t s )
   {
     DPCU_REQUIRE( ctx && results && viewProjections, "NULL argument" );
     DPCU_REQUIRE( nViews >= 1 && nViews <= DPCU_MAX_VIEWS, "nViews must be 1..DPCU_MAX_VIEWS" );
@@ -700,6 +745,15 @@ extern "C"
     {
       DPCU_REQUIRE( results[v] && results[v]->ctx == ctx, "result does not belong to this context" );
       for ( int u = 0; u < v; ++u ) DPCU_REQUIRE( results[u] != results[v], "results must be distinct" );
+      // one kernel stores every view's lines into the peers: all results of a run share one peer layout
+      DPCU_REQUIRE( results[v]->nPeers == results[0]->nPeers && results[v]->peerWordOffset == results[0]->peerWordOffset,
+                    "results of one run must agree on peer count and word offset (dpcuCullResultSetPeerBits)" );
+    }
+    if ( ctx->boundTree )
+    {
+      // bound in place: follow the tree (its arrays may have been reallocated by dpcuTreeSetTopology)
+      ctx->boundMats = static_cast<float const *>( ctx->boundTree->world.ptr );
+      ctx->nMats     = ctx->boundTree->numNodes;
     }
     if ( s != ctx->stream )
     {
@@ -715,12 +769,28 @@ extern "C"
         return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: transform index %u out of range (%zu matrices)",
                            ctx->maxTransformIndex, ctx->nMats );
     }
-    const size_t nSegs = dpcu::divUp( n, size_t( 1 ) << dpcu::kSegObjectsLog2 );
     for ( int v = 0; v < nViews; ++v )
     {
       dpcuCullResult *r = results[v];
+      if ( r->hBits && r->hBitsWords < dpcu::divUp( n, 32 ) )
+        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: host mirror holds %zu bitset words, %zu needed", r->hBitsWords, dpcu::divUp( n, 32 ) );
       DPCU_CUDA( r->done.orderBefore( s ) );      // after this result's previous cull / bit moves, wherever they ran
       DPCU_TRY( dpcu::ensureResultCapacity( r, n, s ) );
+    }
+    return DPCU_OK;
+  }
+
+  // prepareCull has succeeded for the same arguments
+  static int runCull( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, cudaStream_t s, dpcu::LeafArgs const *leaf,
+                      bool treeOnStream = false )
+  {
+    const size_t n = ctx->n;
+    const size_t nSegs = dpcu::divUp( n, size_t( 1 ) << dpcu::kSegObjectsLog2 );
+    // matrices bound to a tree: wait for the compute that produced them (wherever it ran)
+    if ( ctx->boundTree && !treeOnStream ) DPCU_CUDA( ctx->boundTree->done.orderBefore( s ) );
+    for ( int v = 0; v < nViews; ++v )
+    {
+      dpcuCullResult *r = results[v];
       if ( r->n != n )
       {
         size_t words = dpcu::divUp( r->n > n ? r->n : n, 32 );
@@ -734,8 +804,6 @@ extern "C"
       r->nSegs = nSegs;
       r->ran = true;
       r->visBuilt = false;
-      if ( r->hBits && r->hBitsWords < dpcu::divUp( n, 32 ) )
-        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: host mirror holds %zu bitset words, %zu needed", r->hBitsWords, dpcu::divUp( n, 32 ) );
     }
     if ( !n )
     {
@@ -776,8 +844,40 @@ extern "C"
       }
       ca.nWords = uint32_t( dpcu::divUp( n, 32 ) );
       ca.nSegs = uint32_t( nSegs );
-      dim3 grid( ca.nSegs, unsigned( nViews ) );
-      dpcu::compactChangedKernel<<<grid, 256, 0, s>>>( ca );
+      // programmatic dependent launch: the compaction CTAs are placed while the cull kernel drains and wait in
+      // cudaGridDependencySynchronize() for its memory - the launch latency of the second kernel is off the critical
+      // path (it was a quarter of the step at 1 Mi objects)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim  = dim3( ca.nSegs, unsigned( nViews ) );
+      cfg.blockDim = dim3( 256 );
+      cfg.stream   = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      DPCU_CUDA( cudaLaunchKernelEx( &cfg, dpcu::compactChangedKernel, ca ) );
+      ++ctx->launches;
+    }
+    if ( leaf && results[0]->nPeers > 0 )
+    {
+      // C3 on several GPUs: the fused leaf kernel writes this shard's words locally; one small kernel then stores
+      // them as whole lines into every peer's full bitset (NVLink).  2 MB at 16 Mi objects: microseconds, against
+      // the 1 GB re-read of the world matrices that un-fusing the leaf level would cost.
+      dpcu::PeerGatherArgs ga;
+      memset( &ga, 0, sizeof ga );
+      ga.nViews = nViews;
+      ga.nPeers = uint32_t( results[0]->nPeers );
+      ga.nWords = uint32_t( dpcu::divUp( n, 32 ) );
+      ga.wordOffset = uint32_t( results[0]->peerWordOffset );
+      for ( int v = 0; v < nViews; ++v )
+      {
+        ga.bits[v] = static_cast<uint32_t const *>( results[v]->bits.ptr );
+        for ( int p = 0; p < dpcu::kMaxPeers; ++p ) ga.peer[v][p] = p < results[v]->nPeers ? results[v]->peer[p] : nullptr;
+      }
+      unsigned blocks = unsigned( dpcu::divUp( dpcu::divUp( ga.nWords, 4 ), 256 ) );
+      if ( blocks > unsigned( ctx->smCount ) * 4u ) blocks = unsigned( ctx->smCount ) * 4u;
+      dpcu::peerGatherKernel<<<dim3( blocks ? blocks : 1u, unsigned( nViews ) ), 256, 0, s>>>( ga );
       DPCU_CUDA( cudaGetLastError() );
       ++ctx->launches;
     }
@@ -792,6 +892,8 @@ extern "C"
     }
     for ( int v = 0; v < nViews; ++v ) DPCU_CUDA( results[v]->done.record( s ) );
     if ( s != ctx->stream ) DPCU_CUDA( ctx->lastRun.record( s ) );
+    // the tree's next compute must not overwrite the world matrices under this cull
+    if ( ctx->boundTree && !treeOnStream ) DPCU_CUDA( ctx->boundTree->readers.record( s ) );
     return DPCU_OK;
   }
 
@@ -802,7 +904,9 @@ extern "C"
   {
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     dpcu::DeviceGuard guard( ctx->device );
-    return runCull( ctx, results, viewProjections, nViews, stream ? stream->stream : ctx->stream, nullptr );
+    cudaStream_t s = stream ? stream->stream : ctx->stream;
+    DPCU_TRY( prepareCull( ctx, results, viewProjections, nViews, s ) );
+    return runCull( ctx, results, viewProjections, nViews, s, nullptr );
   }
 
   int dpcuCullRunWithTree( dpcuCull *ctx, dpcuTree *tree, dpcuCullResult *const *results, const float *viewProjections, int nViews,
@@ -814,17 +918,18 @@ extern "C"
     dpcu::DeviceGuard guard( ctx->device );
     cudaStream_t s = stream ? stream->stream : ctx->stream;
     // the culler reads the tree's world matrices in place
+    ctx->boundTree = tree;
     ctx->boundMats = static_cast<float const *>( tree->world.ptr );
     ctx->nMats     = tree->numNodes;
+    // everything that can fail without a launch fails HERE, before the tree's dirty state is touched: a fused cull that
+    // never ran would otherwise leave the leaf level's dirty bits cleared and its world matrices stale
+    DPCU_TRY( prepareCull( ctx, results, viewProjections, nViews, s ) );
     const size_t levels = tree->levelOffsets.empty() ? 0 : tree->levelOffsets.size() - 1;
     // can the last level run inside the cull kernel?  object i <-> entry i of that level
     bool fuse = false;
     size_t lastFirst = 0;
-    // peer bitsets (multi-GPU gather) are stored by the line-granular kernel: with peers the tree is propagated
-    // level by level and the cull follows as its own launch
-    bool peers = false;
-    if ( results ) for ( int v = 0; v < nViews && v < DPCU_MAX_VIEWS; ++v ) peers = peers || ( results[v] && results[v]->nPeers > 0 );
-    if ( levels >= 1 && ctx->n && ctx->optFuseLeaf && !ctx->optFma && !peers )
+    // (peer bitsets - the multi-GPU gather - follow the fused kernel as one small copy kernel, see runCull)
+    if ( levels >= 1 && ctx->n && ctx->optFuseLeaf && !ctx->optFma )
     {
       lastFirst = tree->levelOffsets[levels - 1];
       const size_t lastCount = tree->levelOffsets[levels] - lastFirst;
@@ -858,9 +963,11 @@ extern "C"
     leaf.world      = static_cast<float4 *>( tree->world.ptr );
     leaf.dirtyLocal = static_cast<uint32_t const *>( tree->dirtyLocal.ptr );
     leaf.dirtyWorld = static_cast<uint32_t *>( tree->dirtyWorld.ptr );
-    int rc = runCull( ctx, results, viewProjections, nViews, s, fuse ? &leaf : nullptr );
+    int rc = runCull( ctx, results, viewProjections, nViews, s, fuse ? &leaf : nullptr, true );
     if ( fuse && rc == DPCU_OK ) ++tree->launches;        // the fused kernel is the tree's last level too
-    // close the tree's compute even if the cull failed, so its dirty state stays consistent
+    // a fused cull that failed at launch has not propagated the last level: do it now, so that closing the compute
+    // (which clears the dirty bits) leaves no stale world matrix behind
+    if ( fuse && rc != DPCU_OK ) dpcu::treeComputeLevels( tree, s, levels - 1, levels );
     int rc2 = dpcu::treeEndCompute( tree, s );
     return rc != DPCU_OK ? rc : rc2;
   }
@@ -1140,7 +1247,7 @@ extern "C"
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     switch ( option )
     {
-      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( ( value >= 0 && value <= 5 ) || value == DPCU_KERNEL_LINES_PAIRS, "kernel must be 0..5 or 7" ); ctx->optKernel = value; break;
+      case DPCU_CULL_OPT_KERNEL:       DPCU_REQUIRE( ( value >= 0 && value <= 5 ) || value == DPCU_KERNEL_LINES_PAIRS || value == DPCU_KERNEL_GRID, "kernel must be 0..5, 7 or 8" ); ctx->optKernel = value; break;
       case DPCU_CULL_OPT_FMA:          ctx->optFma = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CHANGED_LIST: ctx->optChanged = value ? 1 : 0; break;
       case DPCU_CULL_OPT_CTAS_PER_SM:  DPCU_REQUIRE( value >= 0 && value <= 32, "ctas per SM must be 0..32" ); ctx->optCtasPerSm = value; break;

@@ -241,6 +241,14 @@ extern "C"
     return DPCU_OK;
   }
 
+  int dpcuBufferFillAsync( dpcuBuffer *buffer, int byteValue, size_t bytes, size_t offset, dpcuStream *stream )
+  {
+    DPCU_REQUIRE( buffer && stream, "NULL argument" );
+    DPCU_REQUIRE( offset + bytes <= buffer->size, "range exceeds buffer size" );
+    if ( bytes ) DPCU_CUDA( cudaMemsetAsync( static_cast<char *>( buffer->devicePointer ) + offset, byteValue, bytes, stream->stream ) );
+    return DPCU_OK;
+  }
+
   // ------------------------------------------------------------------ pinned host buffer
   int dpcuHostBufferCreate( dpcuHostBuffer **out, size_t bytes, unsigned flags )
   {

@@ -137,6 +137,7 @@ namespace dpcu
       DPCU_CUDA( t->uploads.orderBefore( s ) );
     }
     DPCU_CUDA( t->done.orderBefore( s ) );
+    DPCU_CUDA( t->readers.orderBefore( s ) );          // a cull may still be reading the world matrices in place
     size_t words = divUp( t->numNodes, 32 );
     // the previous compute's published set is dropped now (the reference clears it right after notifying, Tree.cpp:163-164)
     DPCU_CUDA( cudaMemsetAsync( t->dirtyWorld.ptr, 0, words * 4, s ) );
@@ -209,8 +210,10 @@ extern "C"
     dpcu::DeviceGuard guard( t->device );
     cudaStreamSynchronize( t->stream );
     t->done.hostWait();
+    t->readers.hostWait();
     t->done.destroy();
     t->uploads.destroy();
+    t->readers.destroy();
     t->local.release(); t->world.release(); t->entries.release(); t->dirtyLocal.release(); t->dirtyWorld.release(); t->scratch.release();
     cudaStreamDestroy( t->stream );
     delete t;

@@ -19,6 +19,7 @@ struct dpcuTree
   uint64_t     launches = 0;
   uint64_t     topologyVersion = 0;   // bumped by dpcuTreeSetTopology (cached leaf bindings of cull contexts go stale)
   dpcu::StreamFence done;        // last compute submitted
+  dpcu::StreamFence readers;     // last cull that read `world` in place (dpcuCullBindTree / dpcuCullRunWithTree): the next compute waits for it
   dpcu::StreamFence uploads;
 };
 

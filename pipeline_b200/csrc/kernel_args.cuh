@@ -23,6 +23,7 @@ namespace dpcu
     uint32_t *changed;          // out: ascending group indices
     uint32_t *hostChanged;      // optional mirrors in pinned host memory
     uint32_t *hostCount;
+    uint32_t *gridTotals;        // cullGridKernel: flips per CTA (the grid-wide prefix of phase 2)
     uint32_t *peer[kMaxPeers];   // optional: full bitsets on peer GPUs (NVLink stores)
   };
 

@@ -57,8 +57,13 @@ namespace dpcu
       const uint32_t need   = first == 31u ? 0xffffffffu : ( ( 2u << first ) - 1u );
       if ( ( vmask & need ) != need )
       {
-        // a predecessor in the window has not published yet: it is running on some other warp; poll again
-        if ( ++polls > ( 1u << 24 ) ) __trap();            // fail loudly instead of hanging the device
+        // a predecessor in the window has not published yet: it is running on some other warp.  Back off (the waiting
+        // warp must not take issue slots from the one it waits for) and poll again.  A predecessor can legitimately be
+        // away for long - preemption under MPS / a debugger, a stalled PCIe or NVLink store - so the walk only gives up
+        // after ~30 s of sleeping (2^25 polls of up to 1 us), where a trap is better than a silently hung device.
+        ++polls;
+        __nanosleep( polls < 8u ? 32u : ( polls < 64u ? 256u : 1024u ) );
+        if ( polls > ( 1u << 25 ) ) __trap();
         continue;
       }
       uint32_t v = ( lane <= first ) ? uint32_t( s ) : 0u;

@@ -25,6 +25,9 @@ namespace dpcu
     const uint32_t v    = blockIdx.y;
     const uint32_t s    = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // launched with programmatic stream serialization behind the cull kernel: wait for its results here
+    // (a no-op when the launch carries no such dependency, e.g. behind segmentPopcountKernel)
+    cudaGridDependencySynchronize();
     const uint32_t base0 = a.prefix[v][s];
     const uint32_t count = a.prefix[v][s + 1] - base0;
     if ( s == 0 && threadIdx.x == 0 && a.hostCount[v] ) *a.hostCount[v] = a.prefix[v][a.nSegs];
@@ -225,6 +228,42 @@ namespace dpcu
       {
         atomicMin( keys + k, orderedKey( b.lo[k] ) );
         atomicMax( keys + 3 + k, orderedKey( b.hi[k] ) );
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Multi-GPU gather behind the fused leaf kernel (C3 sharded over several GPUs): this GPU's
+  // finished bitset words into every peer's full bitset at the shard's word offset, 16 bytes per thread
+  // where the alignment allows (shard offsets are whole 128-byte lines, pipeline_b200/sharding.py).
+  struct PeerGatherArgs
+  {
+    uint32_t const *bits[8];
+    uint32_t       *peer[8][kMaxPeers];
+    int             nViews;
+    uint32_t        nPeers, nWords, wordOffset;
+  };
+
+  __global__ void __launch_bounds__( 256 ) peerGatherKernel( const __grid_constant__ PeerGatherArgs a )
+  {
+    const int v = blockIdx.y;
+    uint32_t const *src = a.bits[v];
+    const bool wide = ( a.wordOffset & 3u ) == 0;
+    const uint32_t nQuads = wide ? a.nWords >> 2 : 0u;
+    for ( uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nQuads; q += gridDim.x * blockDim.x )
+    {
+      const uint4 w = reinterpret_cast<uint4 const *>( src )[q];
+      for ( uint32_t p = 0; p < a.nPeers; ++p )
+      {
+        if ( a.peer[v][p] ) reinterpret_cast<uint4 *>( a.peer[v][p] + a.wordOffset )[q] = w;
+      }
+    }
+    for ( uint32_t k = ( nQuads << 2 ) + blockIdx.x * blockDim.x + threadIdx.x; k < a.nWords; k += gridDim.x * blockDim.x )
+    {
+      const uint32_t w = src[k];
+      for ( uint32_t p = 0; p < a.nPeers; ++p )
+      {
+        if ( a.peer[v][p] ) a.peer[v][p][a.wordOffset + k] = w;
       }
     }
   }

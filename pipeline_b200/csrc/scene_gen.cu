@@ -65,3 +65,33 @@ extern "C" int dpcuSceneGenerate( uint64_t seed, uint64_t first, size_t count, u
   DPCU_CUDA( cudaGetLastError() );
   return DPCU_OK;
 }
+
+// Bench support: read `bytes` of device memory once (streaming loads, result discarded).  After bench.py's L2 flush
+// WRITE (a buffer larger than L2) this sweep over a second buffer leaves the L2 cold AND clean, so that the write-back
+// of the flush's own dirty lines does not land inside the next timed step.
+namespace dpcu
+{
+  __global__ void __launch_bounds__( 256 ) readSweepKernel( uint4 const *p, size_t n, uint32_t *sink )
+  {
+    uint32_t acc = 0;
+    for ( size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x; i < n; i += size_t( gridDim.x ) * blockDim.x )
+    {
+      const uint4 v = __ldcg( p + i );
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if ( acc == 0x9e3779b9u ) *sink = acc;                   // keeps the loads alive; practically never taken
+  }
+}
+
+extern "C" int dpcuDebugReadSweep( const void *deviceMemory, size_t bytes, dpcuStream *stream )
+{
+  DPCU_TRY( dpcu::requireDevice() );
+  DPCU_REQUIRE( deviceMemory && bytes >= 16 && ( reinterpret_cast<uintptr_t>( deviceMemory ) & 15 ) == 0, "need a 16-byte aligned device buffer" );
+  int device = 0, sms = 1;
+  DPCU_CUDA( cudaGetDevice( &device ) );
+  cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, device );
+  uint32_t *sink = reinterpret_cast<uint32_t *>( const_cast<void *>( deviceMemory ) );
+  dpcu::readSweepKernel<<<sms * 8, 256, 0, stream ? stream->stream : 0>>>( static_cast<uint4 const *>( deviceMemory ), bytes / 16, sink );
+  DPCU_CUDA( cudaGetLastError() );
+  return DPCU_OK;
+}

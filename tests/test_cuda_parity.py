@@ -208,7 +208,7 @@ def test_multi_view_equals_single_views(capi, port):
 # every exact form of K2: DPCU_KERNEL_* plus, for the line-granular kernel, how the changed list is built
 # (inside the kernel by single-pass look-back, the default, or by segment counters + the compaction kernel)
 KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4, "lines_w8": 4,
-           "lines_pairs": 7, "lines_pairs_compact": 7}
+           "lines_pairs": 7, "lines_pairs_compact": 7, "grid": 8}
 
 
 def _select_kernel(capi, ctx, kernel):
@@ -446,10 +446,9 @@ def test_tree_feeds_cull_zero_copy(capi, port):
     for frame in range(3):
         local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=frame * 10)
         t.set_locals(0, local)
-        t.compute()
-        ptr, cnt = t.world_ptr()
-        ctx.bind_matrices(ptr, cnt)
-        ctx.run([r], vp)
+        t.compute()                                 # on the tree's own stream ...
+        ctx.bind_tree(t)                            # ... the binding orders the cull (context stream) after it, and the next
+        ctx.run([r], vp)                            # compute after the cull: events, no host synchronisation in between
         dl = np.full(nw, 0xFFFFFFFF, np.uint32)
         dw = np.zeros(nw, np.uint32)
         port.tree_compute(local, world, entries, offsets, dl, dw)
@@ -672,7 +671,7 @@ class _Mirror:
 
 
 @pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact", "lines_w8", "lines_pairs",
-                                    "lines_pairs_compact"])
+                                    "lines_pairs_compact", "grid"])
 @pytest.mark.parametrize("nv", [1, 3])
 def test_host_mirror_matches_port(capi, port, kernel, nv):
     """dpcuCullResultSetHostMirror: after run + synchronize the pinned buffers hold exactly what
@@ -769,9 +768,10 @@ def test_host_mirror_capacity_and_errors(capi, port):
     r.close(), ctx.close(), m.close(), small.close()
 
 
-def test_run_with_tree_and_peer_bitsets(capi, port):
-    """C3 on several GPUs: with peer bitsets set, dpcuCullRunWithTree propagates the whole tree and hands the cull
-    to the line-granular kernel (which stores the lines into the peers) instead of fusing the leaf level."""
+@pytest.mark.parametrize("fuse", [1, 0])
+def test_run_with_tree_and_peer_bitsets(capi, port, fuse):
+    """C3 on several GPUs: with peer bitsets set, dpcuCullRunWithTree keeps the leaf level fused into the cull and a small
+    copy kernel stores the shard's words into the peers; with fusion off the line-granular kernel stores them itself."""
     levels = (4, 32, 1024)
     entries, offsets, n_nodes = scenes.hierarchy_topology(levels)
     n = levels[-1]
@@ -785,6 +785,7 @@ def test_run_with_tree_and_peer_bitsets(capi, port):
     t.set_topology(entries, offsets, n_nodes)
     t.set_locals(0, local)
     ctx = capi.Cull(0)
+    ctx.set_option(capi.OPT_FUSE_LEAF, fuse)
     ctx.set_objects(lower4, extent4, tidx)
     r = ctx.result_create()
     words = (n + 31) // 32
@@ -794,7 +795,7 @@ def test_run_with_tree_and_peer_bitsets(capi, port):
     view = scenes.make_look_at((0, 0, 150), (0, 0, 0), (0, 1, 0))
     vp = scenes.mat_mul(view, scenes.make_perspective(40.0, 1.3, 1.0, 500.0))
     ctx.run_with_tree(t, [r], vp)
-    assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_LINES
+    assert ctx.get_option(capi.OPT_LAST_KERNEL) == (capi.KERNEL_FUSED_LEAF if fuse else capi.KERNEL_LINES)
     world = np.zeros_like(local)
     world[0] = np.eye(4, dtype=np.float32)
     nw = (n_nodes + 31) // 32
@@ -861,6 +862,9 @@ def test_profiling_and_kernel_choice_queries(capi):
     res3 = [ctx.result_create() for _ in range(3)]
     ctx.run(res3, _views_for(3))
     assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_VIEWS
+    ctx.set_option(capi.OPT_KERNEL, capi.KERNEL_GRID)
+    ctx.run(res3, _views_for(3))
+    assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_GRID
     ctx.set_option(capi.OPT_KERNEL, capi.KERNEL_LINES)
     ctx.run(res3, _views_for(3))
     assert ctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_LINES
@@ -886,7 +890,7 @@ def test_buffers_streams_events(capi):
     assert s.completed()
     assert np.array_equal(out, a)
     assert e0.elapsed_ms(e1) >= 0.0
-    b.fill(0xAB, 16, 4)
+    b.fill(0xAB, nbytes=16, offset=4)
     small = np.zeros(6, np.uint32)
     b.download(small)
     assert small[0] == 0 and small[1] == 0xABABABAB and small[4] == 0xABABABAB and small[5] == 5

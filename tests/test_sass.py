@@ -29,9 +29,40 @@ def sass():
         if m:
             name = m.group(1)
             funcs[name] = []
+            ADDRS[name] = []
         elif name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
             funcs[name].append(line.split("*/", 1)[1].split("/*")[0].strip())
+            ADDRS[name].append(int(re.match(r"\s+/\*([0-9a-f]{4})\*/", line).group(1), 16))
     return funcs
+
+
+ADDRS = {}            # function name -> address of every instruction of its body (parallel to the body list)
+
+
+def _argument_source(name, body, pos, reg):
+    """`reg` is read at `pos` inside a local callee (the code behind a CALL.REL target, e.g. the queued exact pass
+    mvFlush of the multi-view lines kernel) and is not written between the callee's entry and `pos`: it is an incoming
+    argument.  Returns the constant-bank offsets it was loaded from before every call site (None if any call site
+    defines it differently)."""
+    addrs = ADDRS[name]
+    calls = [(k, int(m.group(1), 16)) for k, i in enumerate(body) for m in [re.search(r"CALL\.REL\.NOINC\s+(0x[0-9a-f]+)", i)] if m]
+    targets = sorted({t for _, t in calls if t <= addrs[pos]})
+    if not targets:
+        return None
+    entry = addrs.index(targets[-1])
+    for back in range(pos - 1, entry - 1, -1):
+        d = _DEST.match(body[back])
+        if d and d.group(1) == reg:
+            return None
+    sources = []
+    for k, t in calls:
+        if t != targets[-1]:
+            continue
+        src = _constant_source(body, k, reg)
+        if src is None:
+            return None
+        sources.append(src)
+    return sources
 
 
 def _kernels(funcs, stem):
@@ -81,9 +112,9 @@ def test_exact_kernels_have_no_contracted_multiply_add(sass):
     view-projection entry may be fused."""
     exact = {k: v for k, v in sass.items()
              if any(s in k for s in ("cullDirectKernel", "cullViewsKernel", "cullStagedKernel", "cullLinesKernel",
-                                     "cullFusedLeafKernel", "treeLevelKernel", "treeLevelWideKernel",
+                                     "cullLinesMvKernel", "mvFlush", "cullFusedLeafKernel", "treeLevelKernel", "treeLevelWideKernel",
                                      "boundingBoxKernel")) and "_fma" not in k}
-    assert len(exact) >= 8 * 6 + 3
+    assert len(exact) >= 8 * 7 + 3
     checked_filter = 0
     for name, body in exact.items():
         m = re.search(r"Kernel(?:I|_fmaI)Li(\d)E", name)
@@ -100,10 +131,20 @@ def test_exact_kernels_have_no_contracted_multiply_add(sass):
             if any(src is not None and layout["filter"] <= src < layout["end"] for src in sources):
                 checked_filter += 1                       # (b) the filter's own arithmetic
                 continue
+            if not packed and len(regs) >= 2 and regs[0] == regs[1]:
+                checked_filter += 1                       # (b') a square (the filter's radius): the reference never squares
+                continue
             # (a) addProd
             assert packed, "%s: scalar fused multiply-add outside the filter: %s" % (name, i)
             assert len(ops) == 4 and ops[1].endswith(".F32x2.HI_LO") and ops[1].startswith("R"), "%s: %s" % (name, i)
-            assert ops[2].startswith("UR"), "%s: %s" % (name, i)
+            if not ops[2].startswith("UR"):
+                # the queued exact pass is a local callee: `one` arrives in a register pair, loaded from onePair before each call
+                lo = ops[2].split(".")[0]
+                hi = "R%d" % (int(lo[1:]) + 1)
+                for reg, base in ((lo, layout["one"]), (hi, layout["one"] + 4)):
+                    srcs = _argument_source(name, body, pos, reg)
+                    assert srcs and all(x == base for x in srcs), "%s: FFMA2 multiplier %s is not CullArgs::onePair: %s" % (name, reg, i)
+                continue
             src = _constant_source(body, pos, ops[2].split(".")[0])
             if src is None:                               # a UMOV of a half loaded elsewhere: follow it once
                 for back in range(pos - 1, -1, -1):

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--changed", type=int, default=1)
     ap.add_argument("--filter", type=int, default=1, help="multi-view filter (DPCU_CULL_OPT_FILTER)")
     ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
-    ap.add_argument("--flush", type=int, default=0, help="1: write 256 MiB between iterations (cold L2)")
+    ap.add_argument("--flush", type=int, default=0, help="1: write 256 MiB between iterations (cold, dirty L2); 2: ... then read another 256 MiB (cold, clean L2)")
     a = ap.parse_args()
     n = a.n
     lo, ex, mt = capi.Buffer(n * 16), capi.Buffer(n * 16), capi.Buffer(n * 64)
@@ -54,15 +54,21 @@ def main():
     ctx.set_option(capi.OPT_PROFILE, 1)
     ctx.kernel_time()
     flush = capi.Buffer(256 << 20) if a.flush else None
+    sweep = capi.Buffer(256 << 20) if a.flush == 2 else None
+    # everything is queued without a host synchronisation in between: with a flush (tens of microseconds of device work)
+    # in front of every step the launches are enqueued ahead of the GPU, so a step's event pair brackets device time, not
+    # the CPU's launch overhead
+    evs = [(capi.Event(), capi.Event()) for _ in range(a.iters)]
     for f in range(a.iters):
         if flush is not None:
-            flush.fill(f & 0xFF)
-            capi.device_sync()
-        e0.record(s)
+            flush.fill(f & 0xFF, s)
+            if sweep is not None:
+                capi.read_sweep(sweep.ptr, 256 << 20, s)
+        evs[f][0].record(s)
         ctx.run(res, cam[3 + f], s)
-        e1.record(s)
-        s.sync()
-        times.append(e0.elapsed_ms(e1))
+        evs[f][1].record(s)
+    s.sync()
+    times = [x.elapsed_ms(y) for x, y in evs]
     t = np.median(times)
     k_ms, k_n = ctx.kernel_time()
     nchg = sum(r.changed_count() for r in res) if a.changed else 0
