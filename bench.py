@@ -312,6 +312,8 @@ def run_ours(args, rank, world, local_rank):
     n_total = n_per * world
     first = rank * n_per
     W, K = args.warmup, args.steps
+    if args.workload == "c2":
+        K = max(K, 20)
 
     def barrier():
         if dist is not None:
@@ -322,8 +324,15 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- scene, resident in HBM
     stream = capi.Stream()
     tree = None
+    c3_upper = 0
     if args.workload == "c3":
-        entries, offsets, n_nodes = scenes.hierarchy_topology(C3_LEVELS)
+        from pipeline_b200 import sharding
+        # SURVEY.md 8e "Transform propagation": levels 0..L-2 are replicated (every GPU propagates the 1.1 M upper nodes
+        # itself, no communication), the leaf level is sharded with the objects.  Weak scaling: every GPU gets the full
+        # 16 Mi leaves / objects, i.e. the tree a rank sees is the C3 tree with world x as many leaves in total.
+        levels_total = C3_LEVELS[:-1] + (C3_LEVELS[-1] * world,)
+        entries, offsets, n_nodes, c3_upper, first, cnt_leaves, _ = sharding.tree_shard(levels_total, world, rank)
+        assert cnt_leaves == n_per
         tree = capi.Tree(device)
         if os.environ.get("DPCU_BENCH_TREE_WIDE_MIN"):          # developer A/B of the two K1 forms
             tree.set_option(capi.TREE_OPT_WIDE_MIN_NODES, int(os.environ["DPCU_BENCH_TREE_WIDE_MIN"]))
@@ -332,14 +341,15 @@ def run_ours(args, rank, world, local_rank):
         first_leaf = n_nodes - n_per
         lo, ex = capi.Buffer(n_per * 16), capi.Buffer(n_per * 16)
         scratch = capi.Buffer(n_per * 64)
-        # objects: random boxes; object i is bound to leaf i (transformIndex = first_leaf + i)
-        capi.scene_generate(seed, 0, n_per, (-first_leaf) & 0xFFFFFFFF, lo.ptr, ex.ptr, scratch.ptr)
+        # objects: random boxes; object i of this rank is bound to its leaf i (transformIndex = first_leaf + i)
+        capi.scene_generate(seed, first, n_per, (first - first_leaf) & 0xFFFFFFFF, lo.ptr, ex.ptr, scratch.ptr)
         capi.device_sync()
         scratch.close()
-        # local matrices of every node: rigid transforms from the same generator (bench input only)
+        # local matrices: rigid transforms from the same generator, a function of the GLOBAL node index (bench input only)
         lptr, _ = tree.local_ptr()
         lo2, ex2 = capi.Buffer(n_nodes * 16), capi.Buffer(n_nodes * 16)
-        capi.scene_generate(seed + 1, 0, n_nodes, 0, lo2.ptr, ex2.ptr, lptr)
+        capi.scene_generate(seed + 1, 0, c3_upper, 0, lo2.ptr, ex2.ptr, lptr)
+        capi.scene_generate(seed + 1, c3_upper + first, n_per, 0, lo2.ptr, ex2.ptr, lptr + c3_upper * 64)
         capi.device_sync()
         lo2.close(), ex2.close()
         mats = None
@@ -410,9 +420,11 @@ def run_ours(args, rank, world, local_rank):
     else:
         cams = [np.ascontiguousarray(scenes.orbit_camera(f), np.float32).reshape(1, 16) for f in range(W + 2 * K + 4)]
 
-    flush = None
+    flush = sweep = None
     if n_per * 96 < 200e6:                     # working set fits in the 126 MB L2: flush between timed steps
         flush = capi.Buffer(256 << 20)
+        sweep = capi.Buffer(256 << 20)
+        sweep.fill(1)
 
     def step(f, s=stream):
         if tree is not None:
@@ -442,15 +454,20 @@ def run_ours(args, rank, world, local_rank):
         stream.sync()
         ms_total = e0.elapsed_ms(e1)
     else:
-        ms_total = 0.0
+        # Small workload: every step is bracketed by its own event pair, and in front of it the L2 is flushed - 256 MiB
+        # written (> L2), then another 256 MiB read, so that the L2 is cold AND clean (the write-back of the flush's own
+        # dirty lines must not land inside the timed step).  Everything is queued on the stream without a host
+        # synchronisation in between: the flush keeps the GPU busy while the next step is enqueued, so the event pair
+        # measures device time of the step, not the host's launch overhead.
+        evs = [(capi.Event(), capi.Event()) for _ in range(K)]
         for f in range(K):
-            flush.fill(f & 0xFF)               # > L2 bytes written between timed iterations
-            capi.device_sync()
-            e0.record(stream)
+            flush.fill(f & 0xFF, stream)
+            capi.read_sweep(sweep.ptr, 256 << 20, stream)
+            evs[f][0].record(stream)
             step(W + f)
-            e1.record(stream)
-            stream.sync()
-            ms_total += e0.elapsed_ms(e1)
+            evs[f][1].record(stream)
+        stream.sync()
+        ms_total = float(sum(x.elapsed_ms(y) for x, y in evs))
     barrier()
     sampler.mark("timed1")
     launches1 = ctx.launches() + (tree.launches() if tree else 0)
@@ -549,16 +566,19 @@ def run_ours(args, rank, world, local_rank):
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = alg_bytes / (k_avg_ms / 1000.0) / 1e9
     traffic = None                                       # dram bytes of the same kernel / workload from the committed ncu capture
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_cull_kernel_summary.json")))
+    traffic_source = None
+    for summary in ("r02_cull_kernel_summary.json", "r01_cull_kernel_summary.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", summary)))
+        except Exception:
+            continue
         for p in prof.get("captures", []):
-            if (p.get("workload") == args.workload and p.get("objects") == n_per and p.get("views") == views
+            if (traffic is None and p.get("workload") == args.workload and p.get("objects") == n_per and p.get("views") == views
                     and kernel_name.split("<")[0] in p.get("kernel", "")):
                 traffic = p["dram_bytes_read"] + p["dram_bytes_write"]
-    except Exception:
-        pass
+                traffic_source = "profiles/%s (%s): ncu --set full capture of this kernel on this workload, dram__bytes_read.sum + dram__bytes_write.sum per launch" % (summary, p.get("report", "?"))
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n),
                 "launch_ms_p10_p50_p90": [float(x) for x in np.percentile(k_each, [10, 50, 90])] if len(k_each) else None,
                 "step_share": k_ms / ms_total if ms_total else None}
@@ -572,7 +592,7 @@ def run_ours(args, rank, world, local_rank):
     also = {"e2e_via_copy_getters": {"ms_per_step": copy_ms / K, "objects_per_s": n_total / (copy_ms / K / 1000.0),
                                      "what": "dpcuCullRun, then dpcuCullResultGetBits / GetChanged copies (no host mirror)"}}
     # ---------------- the same step with the bitset all-gather fused into the cull kernel (N > 1)
-    if world > 1 and args.gather == "also" and tree is None:
+    if world > 1 and args.gather == "also":
         if enable_gather():
             for f in range(3):
                 step(f)
@@ -591,13 +611,102 @@ def run_ours(args, rank, world, local_rank):
             kg_ms, kg_n = ctx.kernel_time()
             ok = verify_gather()
             also["with_bitset_allgather"] = {
-                "ms_per_step": ms_g, "objects_per_s": n_total / (ms_g / 1000.0), "kernel": "cullLinesKernel<%d>" % views,
+                "ms_per_step": ms_g, "objects_per_s": n_total / (ms_g / 1000.0),
+                "kernel": "%s<%d>%s" % (capi.KERNEL_NAMES.get(ctx.get_option(capi.OPT_LAST_KERNEL), "?"), views,
+                                        " + peerGatherKernel" if tree is not None else ""),
                 "avg_launch_ms": kg_ms / max(kg_n, 1), "how": gather, "verified_against_nccl_all_gather": ok,
                 "nvlink_bytes_out_per_gpu_per_step": (world - 1) * n_words * 4 * views}
             for v in range(views):
                 results[v].set_peer_bits([], 0)
         gather = "not part of the headline step (no data-path collective); measured separately under also.with_bitset_allgather"
         gather_ok = None
+
+    # ---------------- K4: the group bounding box over the same resident scene (same 96 B/object stream)
+    if tree is None and not args.no_also:
+        ctx.bounding_box()
+        capi.device_sync()
+        t_bb = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            box = ctx.bounding_box()
+            t_bb.append(time.perf_counter() - t0)
+        bb_ms = 1000.0 * float(np.median(t_bb))
+        also["bounding_box"] = {
+            "ms": bb_ms, "objects_per_s": n_per / (bb_ms / 1000.0), "achieved_GBps": n_per * 96.0 / (bb_ms / 1000.0) / 1e9,
+            "frac_of_hbm_peak": n_per * 96.0 / (bb_ms / 1000.0) / 1e9 / peak, "box": [float(x) for x in box],
+            "what": "dpcuCullGetBoundingBox (ManagerBitSet::calculateBoundingBox): one kernel over the object stream + the 24-byte "
+                    "read-back, wall clock of the synchronous call on this rank's slice"}
+
+    # ---------------- FMA fast mode: reporting only (north_star: its boundary-object disagreements are reported separately)
+    if tree is None and rank == 0 and not args.no_also:
+        rep = ctx.fma_report(cams[W + K][0])
+        also["fma_mode"] = {"objects": rep["objects"], "disagreements": rep["disagreements"], "first_indices": rep["first_indices"],
+                            "what": "the same cull with the direct kernel compiled -fmad=true (DPCU_CULL_OPT_FMA = 1) against the exact "
+                                    "product path, same camera: objects whose visibility bit differs; never used for results"}
+
+    # ---------------- BASELINE config 5 next to the headline: 256 Mi objects STRONG-scaled over the N GPUs, with the bitset
+    # all-gather fused into the timed step when N > 1 (the driver's 1/2/4/8 sweep then shows the c5 strong-scaling curve)
+    if args.workload == "c4-single" and not args.no_also and not args.no_c5:
+        n5 = (1 << 28) // world
+        first5 = rank * n5
+        lo5, ex5, mt5 = capi.Buffer(n5 * 16), capi.Buffer(n5 * 16), capi.Buffer(n5 * 64)
+        capi.scene_generate(WORKLOADS["c5"][2], first5, n5, first5, lo5.ptr, ex5.ptr, mt5.ptr)
+        capi.device_sync()
+        ctx5 = capi.Cull(device)
+        ctx5.set_objects(lo5.ptr, ex5.ptr, None, capi.MEM_DEVICE, n=n5)
+        ctx5.bind_matrices(mt5.ptr, n5)
+        ctx5.set_option(capi.OPT_PROFILE, 1)
+        r5 = ctx5.result_create()
+        g5 = "none (1 GPU)"
+        fb5 = None
+        ok5 = None
+        if world > 1:
+            from pipeline_b200 import sharding
+            fb5 = capi.Buffer(sharding.total_words(1 << 28) * 4)
+            fb5.fill(0)
+            handles = sharding.exchange_ipc(dist, capi.ipc_get_handle(fb5.ptr))
+            ptrs5 = [fb5.ptr if r == rank else capi.ipc_open(handles[r]) for r in range(world)]
+            r5.set_peer_bits(ptrs5, sharding.word_offset(first5))
+            g5 = "fused into the cull kernel's epilogue: NVLink peer stores of finished 128-byte lines into all %d full bitsets" % world
+        for f in range(W):
+            ctx5.run([r5], cams[f], stream)
+        stream.sync()
+        ctx5.kernel_time()
+        barrier()
+        e0.record(stream)
+        for f in range(10):
+            ctx5.run([r5], cams[W + f], stream)
+        e1.record(stream)
+        stream.sync()
+        ms5 = e0.elapsed_ms(e1)
+        if dist is not None:
+            t = torch.tensor([ms5], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms5 = float(t.item())
+        ms5 /= 10
+        k5_ms, k5_n = ctx5.kernel_time()
+        if world > 1:
+            barrier()
+            local5 = torch.from_numpy(r5.bits().view(np.int32)).cuda()
+            parts = sharding.allgather_words(dist, local5, (n5 + 31) // 32)
+            want5 = torch.cat(parts).cpu().numpy().view(np.uint32)
+            got5 = np.zeros(sharding.total_words(1 << 28), np.uint32)
+            fb5.download(got5)
+            ok5 = bool(np.array_equal(got5, want5[:len(got5)]))
+            del local5, parts, want5, got5
+        alg5 = n5 * 96.25
+        also["c5_strong"] = {
+            "objects_total": 1 << 28, "objects_per_gpu": n5, "scaling": "strong", "ms_per_step": ms5,
+            "objects_per_s": (1 << 28) / (ms5 / 1000.0),
+            "kernel": "%s<1>" % capi.KERNEL_NAMES.get(ctx5.get_option(capi.OPT_LAST_KERNEL), "?"), "avg_launch_ms": k5_ms / max(k5_n, 1),
+            "frac_of_hbm_peak": alg5 / (k5_ms / max(k5_n, 1) / 1000.0) / 1e9 / peak,
+            "bitset_allgather": g5, "bitset_allgather_verified_against_nccl_all_gather": ok5,
+            "nvlink_bytes_out_per_gpu_per_step": (world - 1) * ((n5 + 31) // 32) * 4,
+            "limiter": "1 GPU: HBM; N > 1: the cull kernel's peer-store epilogue (every finished line goes out N - 1 times over NVLink)"}
+        r5.close()
+        ctx5.close()
+        for b in (lo5, ex5, mt5):
+            b.close()
 
     # ---------------- the same resident scene against six cube-map frusta in one pass (BASELINE config 4)
     if args.workload == "c4-single" and not args.no_also:
@@ -639,7 +748,7 @@ def run_ours(args, rank, world, local_rank):
                    "matrices": "one per object (transformIndex = i)" if tree is None else "4-level tree, %d nodes" % tree.n_nodes,
                    "camera": "new view-projection every step", "changed_per_step_last": changed,
                    "l2": "inputs (%.1f GB per GPU) larger than L2" % (n_per * 96 / 1e9) if flush is None
-                         else "256 MiB flush write between timed steps",
+                         else "before every timed step: 256 MiB flush write, then a 256 MiB read sweep (cold, clean L2); one event pair per step",
                    "parallelism": "object slices, one per GPU, no data-path collective" if world > 1 else "single GPU",
                    "bitset_allgather": gather, "bitset_allgather_verified": gather_ok,
                    "exact_mode": "-fmad=false, bit-exact vs dp::culling::cpu"},
@@ -677,7 +786,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4-single", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the six-view pass over the same scene")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra measurements over the same scene (six views, c5 strong, K4, FMA report)")
+    ap.add_argument("--no-c5", action="store_true", help="skip also.c5_strong (256 Mi objects over the N GPUs)")
     ap.add_argument("--gather", default="also", choices=["also", "fused", "none"],
                     help="N>1: bitset all-gather through peer stores in the cull kernel's epilogue: measured next to the "
                          "headline step (also, default), inside it (fused), or not at all (none)")

@@ -478,6 +478,34 @@ class Cull:
     def bind_matrices(self, device_ptr, count):
         check(lib().dpcuCullBindMatrices(self.h, device_ptr, count))
 
+    def fma_report(self, vp, limit=16):
+        """north_star: "any fused-multiply-add fast mode must report its boundary-object disagreements separately".
+        Culls the resident scene against `vp` twice into fresh results - exact (-fmad=false) and the reporting-only
+        FMA build of the direct kernel - and returns the objects whose visibility differs."""
+        vp = np.ascontiguousarray(vp, np.float32).reshape(1, 16)
+        exact, fast = self.result_create(), self.result_create()
+        keep = [self.get_option(o) for o in (OPT_FMA, OPT_KERNEL)]
+        try:
+            self.set_option(OPT_FMA, 0)
+            self.run([exact], vp)
+            self.set_option(OPT_FMA, 1)
+            self.set_option(OPT_KERNEL, KERNEL_AUTO)
+            self.run([fast], vp)
+            diff = exact.bits() ^ fast.bits()
+        finally:
+            self.set_option(OPT_FMA, keep[0])
+            self.set_option(OPT_KERNEL, keep[1])
+            exact.close(), fast.close()
+        words = np.flatnonzero(diff)
+        idx = []
+        for w in words:
+            x = int(diff[w])
+            while x:
+                b = (x & -x).bit_length() - 1
+                idx.append(int(w) * 32 + b)
+                x &= x - 1
+        return {"objects": int(self.count()), "disagreements": len(idx), "first_indices": idx[:limit], "indices": idx}
+
     def bind_tree(self, tree):
         """cull out of the tree's world matrices in place; culls and tree computes are ordered by events"""
         check(lib().dpcuCullBindTree(self.h, tree.h))

@@ -22,10 +22,11 @@
 //         w_j <= x_j and not x_j <= -w_j: bit P everywhere, invisible.
 //   E: the reference forms every clip coordinate from at most 8 rounded operations on terms whose
 //   absolute values sum to at most  S = sum_r (|p_r| + |a_r| + |b_r| + |c_r|) * sum_c |P[r][c]|,
-//   so its error is below 8u S / (1 - 8u), u = 2^-24; the filter's own centre / plane / support
-//   arithmetic adds less than another 8u S.  The margin used is 2^-17 S' with
-//   S' = max_r (|p_r| + |a_r| + |b_r| + |c_r|) * sum_r sum_c |P[r][c]| >= S  (at least 8x the sum of the two
-//   errors; one multiply per object and view); supports are bounded by Cauchy-Schwarz with radius and plane
+//   so its error is below 8u S / (1 - 8u), u = 2^-24 (two coordinates enter a compare: 16u S); the filter's own centre /
+//   plane / support arithmetic adds less than another 14u S.  The margin used is 2^-17 S' with
+//   S' = max_{r<3} (|p_r| + |a_r| + |b_r| + |c_r|) * sum_{r<3} sum_c |P[r][c]| + sum_c |P[3][c]| >= S  (the w row of P
+//   only ever multiplies p_w = 1 of an affine OBB; four times the sum of the two errors; one fused multiply-add per
+//   object and view); supports are bounded by Cauchy-Schwarz with radius and plane
 //   norms rounded up.  The centre values come from the centre's clip coordinates (A_x, A_y, A_z, W) =
 //   centre * P:  fN_a = W + A_a,  fP_a = W - A_a,  so (V) reads  W - max_a |A_a| > margin.
 //   A decision is taken only when a comparison is TRUE and only when S' < 2^96 (nothing overflowed,
@@ -51,8 +52,8 @@ namespace dpcu
                        // distinguishable (by constant-bank address) from the reference arithmetic, which never fuses
     float rhoN[3];     // per clip axis a: |(col_a + col_w).xyz|_2 of the view-projection, rounded up (N plane: x + w)
     float rhoP[3];     //                  |(col_w - col_a).xyz|_2, rounded up                        (P plane: w - x)
-    float q;           // 2^-17 * sum_r sum_c |P[r][c]|: margin = q * max(aw, 1) >= 2^-17 S
-    float pad;
+    float q;           // 2^-17 * sum_{r<3} sum_c |P[r][c]|: margin = q * max(aw, 1) + qw >= 2^-17 S
+    float qw;          // 2^-17 * sum_c |P[3][c]|: the translation row only ever multiplies the point's w = 1
   };
 
   __device__ __forceinline__ f32x2 fma2( f32x2 a, f32x2 b, f32x2 c )
@@ -108,7 +109,7 @@ namespace dpcu
     float A[3], W;
     unpack2( lo, A[0], A[1] );
     unpack2( hi, A[2], W );
-    const float m = s.aw * f.q;
+    const float m = fmaf( s.aw, f.q, f.qw );
     const bool sane = m < 6.0e23f;                         // S < 2^96 (q carries the 2^-17): nothing overflowed; false for NaN
     // every value below is finite when m is (|value| <= S), so NaN cannot hide behind fminf / fmaxf
     visible = sane & ( W - fmaxf( fabsf( A[0] ), fmaxf( fabsf( A[1] ), fabsf( A[2] ) ) ) > m );

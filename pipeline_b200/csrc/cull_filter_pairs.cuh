@@ -19,12 +19,16 @@
 // Error budget.  The reference forms a clip coordinate from <= 8 rounded operations on terms whose absolute values sum
 // to at most S = sum_r (|p_r|+|a_r|+|b_r|+|c_r|) sum_c |P[r][c]|; a compare x <= -w involves two coordinates: <= 16u S,
 // u = 2^-24.  The filter's centre (4 roundings), clip coordinates (3 fused steps on <= S) and the combinations with
-// r rho and m add < 14u S.  Used: m = aw q with q = 2^-17 sum_r sum_c |P[r][c]| (rounded up) and
-//   aw = max( |cx| + |cy| + |cz| + 3.25 r , 1 )  >=  max_r (|p_r|+|a_r|+|b_r|+|c_r|)
+// r rho and m add < 14u S.  For an affine OBB the w row of P only ever multiplies p_w = 1, so
+//   S <= aw sum_{r<3} sum_c |P[r][c]| + sum_c |P[3][c]|      with
+//   aw = max( |cx| + |cy| + |cz| + 3.25 r , 1 )  >=  max_{r<3} (|p_r|+|a_r|+|b_r|+|c_r|)
 // (p = centre - (a+b+c)/2 and |a_r| <= |a|_2: each component sum is below |centre_r| + 1.5 (|a|+|b|+|c|) <= |centre_r|
-// + 3 r; the 1 is the w row of an affine OBB), so m >= 128u S: four times the sum of both errors.
+// + 3 r).  Used: m = aw q + qw with q = 2^-17 sum_{r<3} sum_c |P[r][c]| and qw = 2^-17 sum_c |P[3][c]| (rounded up), so
+// m >= 128u S: four times the sum of both errors.  (Keeping the translation row out of the product with aw matters: with
+// the eye 150 units off the scene's centre that row sums to ~600, and charged against aw ~ 2000 it made the margin
+// 40 times larger than needed - a quarter of all pairs undecided, 1.25 -> 1.8 ms per 64 Mi x 6 cull.)
 // Underflow: every product may also lose up to 2^-150 absolutely.  The host disables the filter for a view whose
-// sum sum |P| is below 2^-100 (q = +inf), so m >= 2^-117 always covers it; q is likewise +inf for a view-projection
+// sum sum |P| is below 2^-100 (q = +inf), so m >= q + qw >= 2^-117 always covers it; q is likewise +inf for a view-projection
 // with a non-finite entry or a sum above 2^39, and aw is +inf for objects that are not affine, not finite or beyond
 // 2^40 - then m = +inf, every comparison below is false and the pair is undecided.  (aw carries every NaN of the OBB:
 // it is a SUM of the centre coordinates and the radius, and the select below uses !(aw < 2^40).)
@@ -41,7 +45,8 @@ namespace dpcu
     float2 rhoN[3];    // |(col_a + col_w).xyz|_2, rounded up
     float2 nrhoP[3];   // -|(col_w - col_a).xyz|_2, rounded away from zero
     float2 nrhoW;      // -|col_w.xyz|_2, rounded away from zero
-    float2 q;          // 2^-17 sum sum |P|, rounded up; +inf: this view is never decided by the filter
+    float2 q;          // 2^-17 sum_{r<3} sum_c |P[r][c]|, rounded up; +inf: this view is never decided by the filter
+    float2 qw;         // 2^-17 sum_c |P[3][c]|, rounded up
   };
 
   __device__ __forceinline__ f32x2 sub2( f32x2 a, f32x2 b )
@@ -105,7 +110,7 @@ namespace dpcu
     {
       A[c] = fmaPair( cx, asPair( f.k[c] ), fmaPair( cy, asPair( f.k[4 + c] ), fmaPair( cz, asPair( f.k[8 + c] ), asPair( f.k[12 + c] ) ) ) );
     }
-    const f32x2 m  = mul2( pack2( s.aw, s.aw ), asPair( f.q ) );
+    const f32x2 m  = fmaPair( pack2( s.aw, s.aw ), asPair( f.q ), asPair( f.qw ) );
     const f32x2 hi = add2( A[3], m );                      // W + m
     const f32x2 lo = sub2( A[3], m );                      // W - m
     const f32x2 fr = fmaPair( rr, asPair( f.nrhoW ), A[3] );   // W - r rhoW

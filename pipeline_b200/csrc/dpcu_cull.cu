@@ -233,16 +233,18 @@ namespace dpcu
       f.rhoN[a] = roundUp( sqrt( nN[0] * nN[0] + nN[1] * nN[1] + nN[2] * nN[2] ) * inflate );
       f.rhoP[a] = roundUp( sqrt( nP[0] * nP[0] + nP[1] * nP[1] + nP[2] * nP[2] ) * inflate );
     }
-    double q = 0.0;
-    for ( int r = 0; r < 4; ++r ) q += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
+    double q3 = 0.0;
+    for ( int r = 0; r < 3; ++r ) q3 += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
+    const double qw = fabs( P[3][0] ) + fabs( P[3][1] ) + fabs( P[3][2] ) + fabs( P[3][3] );
+    const double q = q3 + qw;
     // q = +inf switches the filter off for this view (classify: `sane` is false): a non-finite entry, or a sum so small
     // that the relative margin would not cover the ABSOLUTE error of underflowing products (each up to 2^-150; with the
     // sum >= 2^-100 the margin is >= 2^-117), or so large that the margin arithmetic could overflow
     bool finite = true;
     for ( int k = 0; k < 16; ++k ) finite = finite && std::isfinite( vp[k] );
     const bool usable = finite && q >= 7.888609052210118e-31 /* 2^-100 */ && q <= 549755813888.0 /* 2^39 */;
-    f.q = usable ? roundUp( marginScale * q / 131072.0 ) : INFINITY;
-    f.pad = 0.0f;
+    f.q  = usable ? roundUp( marginScale * q3 / 131072.0 ) : INFINITY;
+    f.qw = usable ? roundUp( marginScale * qw / 131072.0 ) : 0.0f;
     memcpy( f.rows, vp, 64 );
   }
 
@@ -265,8 +267,10 @@ namespace dpcu
       ( half ? f.k[4 * r + c].y : f.k[4 * r + c].x ) = vp[4 * r + c];
     }
     const double inflate = 1.0 + 1.0 / 1048576.0;
-    double q = 0.0;
-    for ( int r = 0; r < 4; ++r ) q += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
+    double q3 = 0.0;
+    for ( int r = 0; r < 3; ++r ) q3 += fabs( P[r][0] ) + fabs( P[r][1] ) + fabs( P[r][2] ) + fabs( P[r][3] );
+    const double qw = fabs( P[3][0] ) + fabs( P[3][1] ) + fabs( P[3][2] ) + fabs( P[3][3] );
+    const double q = q3 + qw;
     const bool usable = enabled && finite && q >= 7.888609052210118e-31 /* 2^-100 */ && q <= 549755813888.0 /* 2^39 */;
     for ( int a = 0; a < 3; ++a )
     {
@@ -283,7 +287,8 @@ namespace dpcu
     }
     const float rw = usable ? roundAway( -sqrt( P[0][3] * P[0][3] + P[1][3] * P[1][3] + P[2][3] * P[2][3] ) * inflate ) : 0.0f;
     ( half ? f.nrhoW.y : f.nrhoW.x ) = rw;
-    ( half ? f.q.y : f.q.x ) = usable ? roundUp( marginScale * q / 131072.0 ) : INFINITY;
+    ( half ? f.q.y : f.q.x )   = usable ? roundUp( marginScale * q3 / 131072.0 ) : INFINITY;
+    ( half ? f.qw.y : f.qw.x ) = usable ? roundUp( marginScale * qw / 131072.0 ) : 0.0f;
   }
 
   template <int NV>

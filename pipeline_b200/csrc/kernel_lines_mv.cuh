@@ -27,9 +27,9 @@ namespace dpcu
 #endif
 #ifndef DPCU_MV_PIPE
 #define DPCU_MV_PIPE 1              // 0: loads as they come, 1: transform index a step ahead, 2: 1 + L2 prefetch of the next
-#endif                              // step's matrix, 3: all six loads a step ahead (register double buffer)
-#ifndef DPCU_MV_CLAMP
-#define DPCU_MV_CLAMP 1             // lanes past the end re-read the last object instead of branching around the loads
+#endif                              // step's matrix  (all six loads a step ahead - a register double buffer - spilled: 1.9 ms)
+#ifndef DPCU_MV_RECOMPUTE_W
+#define DPCU_MV_RECOMPUTE_W 0       // the OBB's w components are not kept in registers across the classification
 #endif
 #ifndef DPCU_MV_APPEND
 #define DPCU_MV_APPEND 1            // 0: undecided pairs queued view by view (a branch per view), 1: one branch per step
@@ -86,8 +86,10 @@ namespace dpcu
   {
     constexpr int kPairs = ( NV + 1 ) / 2;
     const uint32_t lane   = threadIdx.x & 31u;
-    const uint32_t below  = ( 1u << lane ) - 1u;
-    const uint32_t nWords = ( a.n + 31u ) >> 5, nLines = ( nWords + 31u ) >> 5;
+#define below ( ( 1u << lane ) - 1u )
+    // (recomputed from the kernel argument where needed: as variables they were what ptxas spilled inside the step loop)
+#define nWords ( ( a.n + 31u ) >> 5 )
+#define nLines ( ( ( ( a.n + 31u ) >> 5 ) + 31u ) >> 5 )
     const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
     uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 );
     uint32_t pending = kNoLine;
@@ -135,80 +137,31 @@ namespace dpcu
         idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i0 ) + 3 );
       }
 #endif
-#if DPCU_MV_PIPE == 3
-      // ... and the loads themselves run one step ahead of the arithmetic (register double buffer)
-      uint32_t idxNext2 = 0;
-      float4 nLo, nEx, nM0, nM1, nM2, nM3;
-      nLo = nEx = nM0 = nM1 = nM2 = nM3 = make_float4( 0.f, 0.f, 0.f, 0.f );
-      {
-        const uint32_t i0 = ( word0 << 5 ) + lane, i1 = i0 + 32u;
-        if ( steps > 1 && i1 < a.n ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
-        if ( i0 < a.n )
-        {
-          float4 const *m = a.mats + 4ull * idxNext;
-          nLo = ldStream( a.lowerIdx + i0 ); nEx = ldStream( a.extent + i0 );
-          nM0 = __ldg( m + 0 ); nM1 = __ldg( m + 1 ); nM2 = __ldg( m + 2 ); nM3 = __ldg( m + 3 );
-        }
-      }
-#endif
 #pragma unroll 1
       for ( uint32_t w = 0; w < steps; ++w )
       {
         const uint32_t i    = ( ( word0 + w ) << 5 ) + lane;
         const bool     live = i < a.n;
         const uint32_t liveMask = __ballot_sync( 0xffffffffu, live );
-        Obb obb;
-#if DPCU_MV_PIPE == 3 || !DPCU_MV_CLAMP
-        obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );   // not affine: never decided, masked by liveMask
-#endif
-        uint32_t tidx = 0;
-#if DPCU_MV_PIPE == 3
-        {
-          const float4 lo = nLo, ex = nEx, m0 = nM0, m1 = nM1, m2 = nM2, m3 = nM3;
-          tidx = idxNext;
-          const uint32_t i1 = i + 32u, i2 = i + 64u;
-          idxNext = idxNext2;
-          if ( w + 1 < steps && i1 < a.n )
-          {
-            float4 const *m = a.mats + 4ull * idxNext;
-            nLo = ldStream( a.lowerIdx + i1 ); nEx = ldStream( a.extent + i1 );
-            nM0 = __ldg( m + 0 ); nM1 = __ldg( m + 1 ); nM2 = __ldg( m + 2 ); nM3 = __ldg( m + 3 );
-          }
-          if ( w + 2 < steps && i2 < a.n ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i2 ) + 3 );
-          if ( live ) obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
-        }
-#else
-#if DPCU_MV_CLAMP
         // lanes past the end re-read the last object (no branch, no zero fill); liveMask drops their results
         const uint32_t ic = min( i, a.n - 1u );
-        {
-#else
-        const uint32_t ic = i;
-        if ( live )
-        {
-#endif
 #if DPCU_MV_PIPE >= 1
-          tidx = idxNext;
+        const uint32_t tidx = idxNext;
 #endif
-          const float4 lo = ldStream( a.lowerIdx + ic );
-          const float4 ex = ldStream( a.extent + ic );
+        const float4 lo = ldStream( a.lowerIdx + ic );
+        const float4 ex = ldStream( a.extent + ic );
 #if DPCU_MV_PIPE == 0
-          tidx = __float_as_uint( lo.w );
+        const uint32_t tidx = __float_as_uint( lo.w );
 #endif
-          float4 const *m = a.mats + 4ull * tidx;
-          const float4 m0 = __ldg( m + 0 );
-          const float4 m1 = __ldg( m + 1 );
-          const float4 m2 = __ldg( m + 2 );
-          const float4 m3 = __ldg( m + 3 );
+        float4 const *m = a.mats + 4ull * tidx;
+        const float4 m0 = __ldg( m + 0 );
+        const float4 m1 = __ldg( m + 1 );
+        const float4 m2 = __ldg( m + 2 );
+        const float4 m3 = __ldg( m + 3 );
 #if DPCU_MV_PIPE >= 1
-          {
-            const uint32_t i1 = min( i + 32u, a.n - 1u );
-            if ( w + 1 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
-          }
+        if ( w + 1 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 32u, a.n - 1u ) ) + 3 );
 #endif
-          obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
-        }
-#endif
+        Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
 #if DPCU_MV_PREFETCH
         {
           // step w + DIST of this line: object runs always; matrices when this step's indices are consecutive
@@ -307,6 +260,25 @@ namespace dpcu
           if ( openMask )
           {
             const uint32_t slot = nObj + __popc( bh & below );
+            // The w components of the OBB do not stay in registers across the classification (4 registers that made
+            // the 6-view instantiation spill): an object the filter handles is affine - they are exactly 1, 0, 0, 0 -
+            // and for the others (aw = +inf: projective, NaN / Inf or huge) they are computed again from the inputs,
+            // with the operations of makeObb.
+#if DPCU_MV_RECOMPUTE_W
+            float4 wv = make_float4( 1.0f, 0.0f, 0.0f, 0.0f );
+            if ( !( ball.aw < __int_as_float( 0x7f800000 ) ) )
+            {
+              const float4 lo = ldStream( a.lowerIdx + ic );
+              const float4 ex = ldStream( a.extent + ic );
+              float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
+              const float w0 = __ldg( &m[0].w ), w1 = __ldg( &m[1].w ), w2 = __ldg( &m[2].w ), w3 = __ldg( &m[3].w );
+              wv.x = ( ( lo.x * w0 + lo.y * w1 ) + lo.z * w2 ) + w3;
+              wv.y = w0 * ex.x;
+              wv.z = w1 * ex.y;
+              wv.w = w2 * ex.z;
+            }
+            obb.pt.w = wv.x; obb.ax.w = wv.y; obb.ay.w = wv.z; obb.az.w = wv.w;
+#endif
             sh.obb[0][slot] = obb.pt; sh.obb[1][slot] = obb.ax; sh.obb[2][slot] = obb.ay; sh.obb[3][slot] = obb.az;
             sh.pos[slot] = uint16_t( ( w << 5 ) | lane );
             uint32_t t = nPairs + pre, m = openMask;
@@ -379,5 +351,8 @@ namespace dpcu
     if ( kFuseList && a.buildChanged && pending != kNoLine ) resolveLine<NV>( a, pending, nLines, nWords, lane );
     if ( kFuseList ) rearmInLastCta( a.done );
     else if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+#undef nWords
+#undef below
+#undef nLines
   }
 }

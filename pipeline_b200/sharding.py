@@ -7,6 +7,9 @@ the gloo backend (tests/test_sharding_gloo.py).
 * ``word_offset``        - where a slice's words go inside the full bitset.
 * ``merge_changed``      - per-rank changed lists (local indices, ascending) -> one global
                            ascending list: concatenation in rank order is already sorted.
+* ``tree_shard``         - the transform hierarchy of one rank (SURVEY.md 8e "Transform propagation"): levels
+                           0..L-2 replicated (every GPU propagates them redundantly, no communication), the
+                           leaf level sharded with the objects.
 * ``exchange_ipc``       - all-gather of cudaIpc handles so that every rank can hand the cull
                            kernel its peers' full-bitset buffers (dpcuCullResultSetPeerBits):
                            the bitset all-gather then happens as NVLink stores inside the
@@ -70,3 +73,28 @@ def allgather_words(dist, local_words, words_per_rank, device=None):
     outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(outs, t)
     return outs
+
+
+def tree_shard(levels, world: int, rank: int):
+    """Topology of rank `rank`'s transform tree for a uniform-fan-out hierarchy `levels` (nodes per level, e.g.
+    scenes.hierarchy_topology's): the upper levels whole, and of the last level only the leaves of this rank's
+    object slice [first, first + count) (object i <-> leaf i).
+
+    Returns (entries (E,2) uint32, level_offsets (L+1,) uint32, n_nodes, first_leaf_local, first, count,
+    global_node_of_local) where global_node_of_local maps a node index of the shard tree to its index in the
+    whole tree (local matrices are a function of the global node index)."""
+    from . import scenes
+    levels = tuple(int(x) for x in levels)
+    n_leaves = levels[-1]
+    first, count = shard_range(n_leaves, world, rank)
+    up_entries, up_offsets, n_upper = scenes.hierarchy_topology(levels[:-1])        # incl. the virtual root 0
+    fan = n_leaves // levels[-2]
+    first_parent = n_upper - levels[-2]                                              # first node of level L-2
+    k = np.arange(first, first + count, dtype=np.uint64)
+    parent = (np.uint64(first_parent) + k // np.uint64(fan)).astype(np.uint32)
+    node = (np.uint64(n_upper) + (k - np.uint64(first))).astype(np.uint32)
+    entries = np.concatenate([up_entries, np.stack([parent, node], axis=1)]).astype(np.uint32)
+    offsets = np.concatenate([up_offsets, [up_offsets[-1] + count]]).astype(np.uint32)
+    n_nodes = n_upper + count
+    global_of_local = np.concatenate([np.arange(n_upper, dtype=np.uint64), np.uint64(n_upper) + k])
+    return entries, offsets, n_nodes, n_upper, first, count, global_of_local

@@ -149,3 +149,20 @@ def boundary_views():
     frustum = scenes.mat_mul(scenes.make_look_at((0, 0, 20), (0, 0, 0), (0, 1, 0)), scenes.make_frustum(-0.5, 0.5, -0.5, 0.5, 1.0, 40.0))
     cube = scenes.cube_map_cameras((1.0, 2.0, 3.0))
     return np.ascontiguousarray(np.stack([persp, ortho, ortho8, behind, shifted, frustum, cube[0], cube[3]]), np.float32)
+
+
+VP_SCALES = (1e-44, 1e-40, 1e-38, 1e-35, 1e-31, 1e-30, 1e-29, 1e-20, 1e-8, 1e8, 1e11, 1e12, 1e20, 1e30)
+
+
+def scaled_views():
+    """View-projections multiplied by a common factor over 75 orders of magnitude (perspective and orthographic).
+    The factor does not change the exact result - every clip coordinate scales with it - but it moves the
+    reference's binary32 products into the denormal range at one end (absolute, not relative, rounding error) and
+    towards overflow at the other: the multi-view filter must stand down where its relative margin no longer
+    covers the error (cull_filter_pairs.cuh; the host switches it off below 2^-100 and above 2^39)."""
+    base = boundary_views()
+    out = []
+    for k in (0, 2, 5, 6):                    # integer-plane perspective, orthographic cube, look-at frustum, cube-map face
+        for sc in VP_SCALES:
+            out.append((base[k].astype(np.float64) * sc).astype(np.float32))
+    return np.ascontiguousarray(np.stack(out), np.float32)

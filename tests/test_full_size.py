@@ -61,6 +61,18 @@ class _Scene:
         tidx = np.arange(count, dtype=np.uint32)
         return port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vp)
 
+    def oracle_words_contiguous(self, port, start, count, vp_list, threads=8):
+        """SURVEY.md 8d parity reporting: one contiguous run of >= 2^24 objects, word for word.  The run's inputs are
+        the bytes the GPU culled (downloaded; the sampled slices above pin them to the host replay of the generator),
+        culled by the oracle with `threads` host threads."""
+        lo = self.lo.download(np.empty((count, 4), np.float32), offset=start * 16)
+        ex = self.ex.download(np.empty((count, 4), np.float32), offset=start * 16)
+        mt = self.mt.download(np.empty(count * 16, np.float32), offset=start * 64)
+        tidx = lo[:, 3].copy().view(np.uint32) - np.uint32(start)
+        assert np.array_equal(tidx, np.arange(count, dtype=np.uint32))
+        lo[:, 3] = 1.0
+        return [port.cull_bits(lo, ex, tidx, mt, vp, threads=threads) for vp in vp_list]
+
     def close(self):
         self.ctx.close()
         for b in (self.lo, self.ex, self.mt):
@@ -140,6 +152,13 @@ def test_c4_sixty_four_million_six_views(capi, port):
         for v in range(6):
             _check_slices(sc, port, new[v], vps[v], starts)
             _check_changed(old[v], new[v], res[v].changed(), n)
+        if frame == 1:
+            # one contiguous 2^24-object run of every view against the oracle, word for word (100 M decisions)
+            start, count = 19 * (1 << 20), 1 << 24
+            want = sc.oracle_words_contiguous(port, start, count, list(vps))
+            for v in range(6):
+                bad = np.flatnonzero(new[v][start // 32:(start + count) // 32] != want[v])
+                assert bad.size == 0, "view %d: %d words differ in the contiguous run, first at word %d" % (v, bad.size, start // 32 + bad[0])
         if frame == 0:
             # the six 90-degree frusta from one eye cover all directions: every object is in at least one
             # of them unless it lies beyond the far plane (the scene reaches |x| = 1000 * sqrt(3) > 1500)
@@ -180,6 +199,10 @@ def test_c5_quarter_billion_sharded_equals_whole(capi, port):
     whole = r.bits()
     assert r.changed_count() == n - _popcount(whole)
     _check_slices(sc, port, whole, vp, _slice_starts(n, 4, seed=5))
+    start, count = 150 * (1 << 20) + 7168, 1 << 24               # a contiguous 2^24-object run, word for word
+    want = sc.oracle_words_contiguous(port, start, count, [vp])[0]
+    assert np.array_equal(whole[start // 32:(start + count) // 32], want)
+    del want
     changed = r.changed()
     assert np.array_equal(changed, _set_bits(~whole, n))
     r.close()
@@ -211,11 +234,13 @@ def test_c3_full_tree_and_sixteen_million_objects(capi, port):
     capi.scene_generate(scenes.SEED_C3, 0, n, (-first_leaf) & 0xFFFFFFFF, lo.ptr, ex.ptr, scratch.ptr)
     capi.device_sync()
     scratch.close()
-    lptr, _ = tree.local_ptr()
-    lo2, ex2 = capi.Buffer(n_nodes * 16), capi.Buffer(n_nodes * 16)
-    capi.scene_generate(scenes.SEED_C3 + 1, 0, n_nodes, 0, lo2.ptr, ex2.ptr, lptr)   # locals: rigid placements, node i <- draw i
+    lo2, ex2, locbuf = capi.Buffer(n_nodes * 16), capi.Buffer(n_nodes * 16), capi.Buffer(n_nodes * 64)
+    capi.scene_generate(scenes.SEED_C3 + 1, 0, n_nodes, 0, lo2.ptr, ex2.ptr, locbuf.ptr)   # locals: rigid placements, node i <- draw i
     capi.device_sync()
     lo2.close(), ex2.close()
+    tree.set_locals(0, locbuf.ptr, capi.MEM_DEVICE, count=n_nodes)
+    all_local = locbuf.download(np.empty((n_nodes, 4, 4), np.float32))      # the bytes the GPU propagates, for the oracle below
+    locbuf.close()
     tree.mark_dirty(1, n_nodes - 1)
     ctx = capi.Cull(0)
     ctx.set_objects(lo.ptr, ex.ptr, None, capi.MEM_DEVICE, n=n)
@@ -266,6 +291,49 @@ def test_c3_full_tree_and_sixteen_million_objects(capi, port):
         want = port.cull_bits(lower4, extent4, np.arange(1024, dtype=np.uint32), mini_world[len(nodes) - 1024:].reshape(-1), vp)
         assert np.array_equal(words[s // 32: s // 32 + 32], want), "visibility words at leaf %d" % s
     assert np.array_equal(r.changed(), _set_bits(~words, n))
+    # the WHOLE frame against the oracle - Tree::compute over all 17.9 M nodes, then all 2^24 objects
+    all_world = np.zeros_like(all_local)
+    all_world[0] = np.eye(4, dtype=np.float32)
+    nw_all = (n_nodes + 31) // 32
+    port.tree_compute(all_local, all_world, entries, offsets, np.full(nw_all, 0xFFFFFFFF, np.uint32), np.zeros(nw_all, np.uint32))
+    # C3 on several GPUs: the same frame as 4 shards - upper levels replicated, the leaf level sharded with
+    # the objects, the leaf level still fused into the cull kernel, every shard's words stored into a "peer" full bitset
+    from pipeline_b200 import sharding
+    full = capi.Buffer(sharding.total_words(n) * 4)
+    full.fill(0)
+    for rank in range(4):
+        e, o, nn, first_leaf_local, first, count, gmap = sharding.tree_shard(levels, 4, rank)
+        st = capi.Tree(0)
+        st.set_topology(e, o, nn)
+        st.set_locals(0, np.ascontiguousarray(all_local[:first_leaf_local]))
+        st.set_locals(first_leaf_local, np.ascontiguousarray(all_local[first_leaf + first:first_leaf + first + count]))
+        st.mark_dirty(1, nn - 1)
+        tix = capi.Buffer(count * 4)
+        tix.upload(np.arange(first_leaf_local, nn, dtype=np.uint32))
+        sctx = capi.Cull(0)
+        sctx.set_objects(lo.ptr + first * 16, ex.ptr + first * 16, tix.ptr, capi.MEM_DEVICE, n=count)
+        sr = sctx.result_create()
+        sr.set_peer_bits([full.ptr], sharding.word_offset(first))
+        sctx.run_with_tree(st, [sr], vp)
+        assert sctx.get_option(capi.OPT_LAST_KERNEL) == capi.KERNEL_FUSED_LEAF
+        assert np.array_equal(sr.bits(), words[first // 32:(first + count) // 32]), "shard %d" % rank
+        sr.close(), sctx.close(), st.close(), tix.close()
+    gathered = full.download(np.empty(sharding.total_words(n), np.uint32))
+    assert np.array_equal(gathered, words), "gathered shard bitsets differ from the whole-tree cull"
+    full.close()
+    del all_local, gathered
+    got_world = tree.world(1, n_nodes - 1)
+    assert np.array_equal(got_world.view(np.uint32), all_world[1:].view(np.uint32)), "world matrices differ from the oracle"
+    del got_world
+    lo_h = lo.download(np.empty((n, 4), np.float32))
+    ex_h = ex.download(np.empty((n, 4), np.float32))
+    tidx_h = lo_h[:, 3].copy().view(np.uint32)
+    assert np.array_equal(tidx_h, np.arange(first_leaf, n_nodes, dtype=np.uint32))
+    lo_h[:, 3] = 1.0
+    want_all = port.cull_bits(lo_h, ex_h, tidx_h, all_world.reshape(-1), vp, threads=8)
+    bad = np.flatnonzero(words != want_all)
+    assert bad.size == 0, "%d of %d visibility words differ from the oracle, first at word %d" % (bad.size, len(words), bad[0])
+    del all_world, lo_h, ex_h, want_all
     # nothing dirty: no world matrix is recomputed, the published dirty set is empty, nothing changes
     ctx.run_with_tree(tree, [r], vp)
     assert r.changed_count() == 0

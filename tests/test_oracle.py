@@ -82,6 +82,21 @@ def test_boundary_scene_eight_views(port, golden):
         assert np.array_equal(port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vps[v]), g["bits%d" % v]), v
 
 
+def test_scaled_view_projections(port, golden):
+    """view-projections scaled from 1e-44 to 1e30 (products underflowing to denormals / heading for overflow): the
+    restatement equals the compiled reference's answers for all 56 views"""
+    g = golden("scaledvp20k")
+    lower4, extent4, mats, tidx = cases.affine_boundary_scene(20013, 104)
+    vps = cases.scaled_views()
+    assert len(vps) == 4 * len(cases.VP_SCALES)
+    differing = 0
+    for v in range(len(vps)):
+        want = g["bits%d" % v]
+        assert np.array_equal(port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vps[v]), want), v
+        differing += int(not np.array_equal(want, g["bits%d" % (v - v % len(cases.VP_SCALES) + 8)]))
+    assert differing > 0          # the scaling really changes answers somewhere (else this golden pins nothing new)
+
+
 def test_gather_and_stride(port, golden):
     g = golden("gather5k")
     lower4, extent4, upper4, raw, tidx, stride = cases.gather_case()

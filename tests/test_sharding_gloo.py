@@ -75,3 +75,46 @@ def test_two_rank_gloo_matches_unsharded(tmp_path, port):
         assert np.array_equal(got["bits%d" % f], want)
         assert np.array_equal(got["chg%d" % f], want_changed.astype(np.uint64))
         assert np.all(np.diff(got["chg%d" % f].astype(np.int64)) > 0)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_tree_shards_equal_whole_tree(port, world):
+    """C3 across GPUs: upper levels replicated, leaf level sharded with the objects.  Every rank's
+    shard tree, propagated and culled on its own (the oracle standing in for the GPU), gives the world matrices and
+    the bitset words of its slice of the whole tree."""
+    from pipeline_b200 import scenes
+    levels = (4, 16, 64, 4096)
+    entries, offsets, n_nodes = scenes.hierarchy_topology(levels)
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=3)
+    world_m = np.zeros_like(local)
+    world_m[0] = local[0]
+    nw = (n_nodes + 31) // 32
+    port.tree_compute(local, world_m, entries, offsets, np.full(nw, 0xFFFFFFFF, np.uint32), np.zeros(nw, np.uint32))
+    n = levels[-1]
+    first_leaf = n_nodes - n
+    lower4, extent4, upper4, _, _ = scenes.random_objects(scenes.SEED_C3, 0, n)
+    lower4[:, :3] *= 0.2
+    extent4[:, :3] *= 0.2
+    vp = scenes.mat_mul(scenes.make_look_at((0, 0, 120), (0, 0, 0), (0, 1, 0)), scenes.make_perspective(50.0, 1.5, 1.0, 400.0))
+    whole = port.cull_bits(lower4, extent4, np.arange(first_leaf, n_nodes, dtype=np.uint32), world_m.reshape(-1), vp)
+    assert 0 < int(np.unpackbits(whole.view(np.uint8)).sum()) < n
+    full = np.zeros(sharding.total_words(n), np.uint32)
+    covered = 0
+    for rank in range(world):
+        e, o, nn, first_leaf_local, first, count, gmap = sharding.tree_shard(levels, world, rank)
+        assert first == covered and nn == first_leaf_local + count and len(gmap) == nn
+        covered += count
+        assert len(o) == len(levels) + 1 and o[-1] - o[-2] == count
+        loc = local[gmap.astype(np.int64)]                      # local matrices are a function of the global node index
+        wm = np.zeros_like(loc)
+        wm[0] = loc[0]
+        nws = (nn + 31) // 32
+        port.tree_compute(loc, wm, e, o, np.full(nws, 0xFFFFFFFF, np.uint32), np.zeros(nws, np.uint32))
+        assert np.array_equal(wm[first_leaf_local:].view(np.uint32), world_m[first_leaf + first:first_leaf + first + count].view(np.uint32))
+        tidx = np.arange(first_leaf_local, nn, dtype=np.uint32)
+        words = port.cull_bits(lower4[first:first + count], extent4[first:first + count], tidx, wm.reshape(-1), vp)
+        sharding.place_words(full, words, first)
+    assert covered == n
+    assert np.array_equal(full, whole)

@@ -87,6 +87,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "boundary40k.npz"), **out)
     e.close()
 
+    # 2c. the same kind of scene under view-projections scaled from 1e-44 to 1e30 (underflow / overflow of the products)
+    n = 20000 + 13
+    lower4, extent4, mats, tidx = cases.affine_boundary_scene(n, 104)
+    upper4 = lower4.copy()
+    upper4[:, :3] = lower4[:, :3] + extent4[:, :3]
+    vps = cases.scaled_views()
+    e = RefEngine(ref)
+    e.add(lower4, upper4, tidx)
+    e.set_matrices(mats.reshape(-1))
+    out = {}
+    for v in range(len(vps)):
+        b, _ = e.cull(vps[v])
+        out["bits%d" % v] = b
+    out["inputs"] = digest(lower4, upper4, mats, tidx, vps)
+    np.savez_compressed(os.path.join(OUT, "scaledvp20k.npz"), **out)
+    e.close()
+
     # 3. boundary / non-finite values -----------------------------------------------------------
     lower4, extent4, upper4, mats, tidx, vps = cases.special_case()
     e = RefEngine(ref)

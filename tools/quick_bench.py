@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--changed", type=int, default=1)
     ap.add_argument("--filter", type=int, default=1, help="multi-view filter (DPCU_CULL_OPT_FILTER)")
     ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
+    ap.add_argument("--eye", type=float, nargs=3, default=None, help="multi-view: cube-map eye position")
+    ap.add_argument("--move", type=float, default=0.0, help="multi-view: the eye moves by this much in x per iteration")
     ap.add_argument("--flush", type=int, default=0, help="1: write 256 MiB between iterations (cold, dirty L2); 2: ... then read another 256 MiB (cold, clean L2)")
     a = ap.parse_args()
     n = a.n
@@ -42,6 +44,9 @@ def main():
     e0, e1 = capi.Event(), capi.Event()
 
     def vps(f):
+        if a.views > 1 and (a.eye is not None or a.move):
+            e = a.eye or (0.0, 0.0, 0.0)
+            return scenes.cube_map_cameras((e[0] + a.move * f, e[1], e[2]))[:a.views]
         if a.views > 1:
             return cams[:a.views]
         return scenes.camera_c2() if a.static else scenes.orbit_camera(f)
