@@ -139,6 +139,15 @@ int dpcuCullSetObjects(dpcuCull *ctx, const float *lower4, const float *extent4,
 int dpcuCullSetObjectRange(dpcuCull *ctx, size_t first, size_t count, const float *lower4,
                            const float *extent4, const uint32_t *transformIndex, int memspace);
 int dpcuCullGetObjectCount(const dpcuCull *ctx, size_t *n);
+/* Batched edits of live objects - what a frame of objectSetBoundingBox / objectSetTransformIndex /
+ * groupAddObject / groupRemoveObject (GroupBitSet.cpp:76-119: the last object moves into the freed slot)
+ * amounts to on the device: dpcuCullSetObjectCount grows or shrinks the object arrays KEEPING their
+ * contents, dpcuCullUpdateObjects overwrites objects indices[k] with (lower4[k], extent4[k],
+ * transformIndex[k]) for k < n (host arrays; indices >= the object count are skipped).  One staged
+ * copy and one kernel per call; the caller does not wait for them. */
+int dpcuCullSetObjectCount(dpcuCull *ctx, size_t n);
+int dpcuCullUpdateObjects(dpcuCull *ctx, const uint32_t *indices, size_t n, const float *lower4, const float *extent4,
+                          const uint32_t *transformIndex);
 
 /* groupSetMatrices (dp/culling/src/GroupBitSet.cpp:121-135): copy `count` matrices laid out with
  * `strideBytes` between them (>= 64, multiple of 4) into the context.  The pointer is not retained. */
@@ -221,6 +230,10 @@ int dpcuCullResultSetHostMirror(dpcuCullResult *result, uint32_t *hostBits, size
                                 uint32_t *hostChanged, size_t changedCapacity, uint32_t *hostChangedCount);
 /* block the calling thread until the last cull / bit move submitted for this result is complete */
 int dpcuCullResultSynchronize(dpcuCullResult *result);
+/* Overwrite visibility words of the stored result: words[k] -> word indices[k] (host arrays).  For hosts that
+ * keep a mirror of the bits and apply a frame's bit moves (ResultBitSet::onNotify) there: the touched words
+ * go back in one batch before the next cull instead of one dpcuCullResultMoveBit launch per removed object. */
+int dpcuCullResultUpdateWords(dpcuCullResult *result, const uint32_t *indices, const uint32_t *words, size_t n);
 
 /* ManagerBitSet::getBoundingBox / calculateBoundingBox, scalar branch
  * (dp/culling/src/ManagerBitSet.cpp:151-162,268-306): out6 = lower.xyz, upper.xyz */
@@ -325,6 +338,10 @@ int dpcuTreeWorldDevicePointer(dpcuTree *tree, const float **deviceMatrices, siz
 int dpcuTreeLocalDevicePointer(dpcuTree *tree, float **deviceMatrices, size_t *numNodes);
 int dpcuTreeGetWorld(dpcuTree *tree, size_t first, size_t count, float *hostMatrices);
 int dpcuTreeGetDirtyWorld(dpcuTree *tree, uint32_t *hostWords, size_t nWords);
+/* Refresh a host copy of the world matrices (hostWorld: numNodes x 16 floats, 64-byte stride, e.g.
+ * dp::transform::Tree::m_matricesWorld) for exactly the nodes the last compute changed: the device compacts
+ * them (index + matrix), one transfer brings them over, the host scatters them.  *updated = how many. */
+int dpcuTreeGetWorldDirty(dpcuTree *tree, float *hostWorld, size_t numNodes, size_t *updated);
 int dpcuTreeGetLaunchCount(const dpcuTree *tree, uint64_t *launches);
 /* Tuning knob (never changes results): levels with at least this many nodes are propagated by the
  * persistent one-thread-per-node kernel with coalesced matrix traffic, smaller ones by the

@@ -170,6 +170,17 @@ class RefCull:
     def remove_object(self, index):
         self._chk(self.lib.dpref_cull_remove_object(self.h, index))
 
+    def set_objects_many(self, indices, lower3, upper3, tidx):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        l = np.ascontiguousarray(lower3, np.float32)
+        u = np.ascontiguousarray(upper3, np.float32)
+        t = np.ascontiguousarray(tidx, np.uint32)
+        self._chk(self.lib.dpref_cull_set_objects_many(self.h, len(idx), _up(idx), _fp(l.reshape(-1)), _fp(u.reshape(-1)), _up(t)))
+
+    def remove_objects_many(self, indices):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        self._chk(self.lib.dpref_cull_remove_objects_many(self.h, len(idx), _up(idx)))
+
     def count(self):
         return int(self.lib.dpref_cull_count(self.h))
 
@@ -325,6 +336,9 @@ def _declare_ref(lib):
     lib.dpref_cull_add_objects.argtypes = [C.c_void_p, C.c_size_t, _f32p, _f32p, _u32p]
     lib.dpref_cull_set_object.argtypes = [C.c_void_p, C.c_size_t, _f32p, _f32p, C.c_uint32]
     lib.dpref_cull_remove_object.argtypes = [C.c_void_p, C.c_size_t]
+    if hasattr(lib, "dpref_cull_set_objects_many"):
+        lib.dpref_cull_set_objects_many.argtypes = [C.c_void_p, C.c_size_t, _u32p, _f32p, _f32p, _u32p]
+        lib.dpref_cull_remove_objects_many.argtypes = [C.c_void_p, C.c_size_t, _u32p]
     lib.dpref_cull_count.argtypes = [C.c_void_p]
     lib.dpref_cull_count.restype = C.c_size_t
     lib.dpref_cull_object_id.argtypes = [C.c_void_p, C.c_size_t]

@@ -192,7 +192,7 @@ extern "C"
 
   // Live edit of an object that is already in the group (the CullingImpl CHANGED event,
   // CullingImpl.cpp:198-202).  Because of the quirk above the caller has to force the OBB
-  // cache dirty itself; dpref_cull_touch() below does that through the public API.
+  // cache dirty itself (any add / remove, or groupMatrixChanged, does).
   int dpref_cull_set_object( void * p, size_t groupIndex, float const * lower3, float const * upper3, uint32_t transformIndex )
   {
     Session * s = SESSION( p );
@@ -215,6 +215,41 @@ extern "C"
     {
       dp::culling::ObjectSharedPtr o = s->manager->groupGetObject( s->group, groupIndex );
       s->manager->groupRemoveObject( s->group, o );
+      return 0;
+    }
+    catch ( std::exception const & e ) { s->error = e.what(); return 1; }
+  }
+
+  // a frame's worth of edits in one call (what CullingImpl::onNotify does per CHANGED / REMOVED event, CullingImpl.cpp:186-202),
+  // so that a test can time the backend instead of the ctypes call overhead
+  int dpref_cull_set_objects_many( void * p, size_t n, uint32_t const * groupIndices, float const * lower3, float const * upper3, uint32_t const * transformIndex )
+  {
+    Session * s = SESSION( p );
+    try
+    {
+      for ( size_t i = 0; i < n; ++i )
+      {
+        dp::culling::ObjectSharedPtr o = s->manager->groupGetObject( s->group, groupIndices[i] );
+        dp::math::Box3f box( dp::math::Vec3f( lower3[3*i+0], lower3[3*i+1], lower3[3*i+2] )
+                           , dp::math::Vec3f( upper3[3*i+0], upper3[3*i+1], upper3[3*i+2] ) );
+        s->manager->objectSetBoundingBox( o, box );
+        s->manager->objectSetTransformIndex( o, transformIndex[i] );
+      }
+      return 0;
+    }
+    catch ( std::exception const & e ) { s->error = e.what(); return 1; }
+  }
+
+  int dpref_cull_remove_objects_many( void * p, size_t n, uint32_t const * groupIndices )
+  {
+    Session * s = SESSION( p );
+    try
+    {
+      for ( size_t i = 0; i < n; ++i )
+      {
+        dp::culling::ObjectSharedPtr o = s->manager->groupGetObject( s->group, groupIndices[i] );
+        s->manager->groupRemoveObject( s->group, o );
+      }
       return 0;
     }
     catch ( std::exception const & e ) { s->error = e.what(); return 1; }

@@ -123,6 +123,10 @@ def _declare(L):
         "dpcuCullUpdateMatrices": [_vp, _u32p, C.c_size_t, _vp, C.c_size_t, C.c_int],
         "dpcuCullBindMatrices": [_vp, _vp, C.c_size_t],
         "dpcuCullBindTree": [_vp, _vp],
+        "dpcuCullSetObjectCount": [_vp, C.c_size_t],
+        "dpcuCullUpdateObjects": [_vp, _u32p, C.c_size_t, _vp, _vp, _u32p],
+        "dpcuCullResultUpdateWords": [_vp, _u32p, _u32p, C.c_size_t],
+        "dpcuTreeGetWorldDirty": [_vp, _vp, C.c_size_t, _szp],
         "dpcuCullGetMatrixCount": [_vp, _szp],
         "dpcuCullResultCreate": [_vp, C.POINTER(_vp)],
         "dpcuCullResultDestroy": [_vp],
@@ -386,6 +390,12 @@ class CullResult:
     def move_bit(self, old, new):
         check(lib().dpcuCullResultMoveBit(self.h, old, new))
 
+    def update_words(self, indices, words):
+        """overwrite visibility words of the stored result (a frame's bit moves applied on a host mirror, in one batch)"""
+        idx = np.ascontiguousarray(indices, np.uint32)
+        w = np.ascontiguousarray(words, np.uint32)
+        check(lib().dpcuCullResultUpdateWords(self.h, idx.ctypes.data_as(_u32p), w.ctypes.data_as(_u32p), len(idx)))
+
     def device_pointers(self):
         bits, chg, cnt, nw = _vp(), _vp(), _vp(), C.c_size_t()
         check(lib().dpcuCullResultDevicePointers(self.h, C.byref(bits), C.byref(nw), C.byref(chg), C.byref(cnt)))
@@ -459,6 +469,18 @@ class Cull:
         c = C.c_size_t()
         check(lib().dpcuCullGetObjectCount(self.h, C.byref(c)))
         return c.value
+
+    def set_object_count(self, n):
+        """grow / shrink the object arrays keeping their contents"""
+        check(lib().dpcuCullSetObjectCount(self.h, n))
+
+    def update_objects(self, indices, lower4, extent4, tidx):
+        """one batch of object edits: object indices[k] <- (lower4[k], extent4[k], tidx[k])"""
+        idx = np.ascontiguousarray(indices, np.uint32)
+        lo = np.ascontiguousarray(lower4, np.float32)
+        ex = np.ascontiguousarray(extent4, np.float32)
+        ti = np.ascontiguousarray(tidx, np.uint32)
+        check(lib().dpcuCullUpdateObjects(self.h, idx.ctypes.data_as(_u32p), len(idx), _ptr(lo), _ptr(ex), ti.ctypes.data_as(_u32p)))
 
     def set_matrices(self, mats, stride=64, count=None, memspace=MEM_HOST):
         if count is None:
@@ -626,6 +648,13 @@ class Tree:
         out = np.zeros((count, 4, 4), dtype=np.float32)
         check(lib().dpcuTreeGetWorld(self.h, first, count, _ptr(out)))
         return out
+
+    def refresh_host_world(self, host_world):
+        """scatter the world matrices the last compute changed into host_world ((n_nodes, 4, 4) float32); returns how many"""
+        assert host_world.flags["C_CONTIGUOUS"] and host_world.dtype == np.float32
+        c = C.c_size_t()
+        check(lib().dpcuTreeGetWorldDirty(self.h, host_world.ctypes.data, host_world.size // 16, C.byref(c)))
+        return c.value
 
     def dirty_world(self):
         words = np.zeros((self.n_nodes + 31) // 32, dtype=np.uint32)

@@ -128,6 +128,8 @@ struct dpcuCull
   size_t       n = 0, nMats = 0;
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
+  bool         maxIndexStale = false;    // objects were overwritten / removed since the running maximum was started
+  dpcu::StreamFence stagingFree;         // the last upload out of `staging` (the next user waits for it, not the caller)
   int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1, optLineWords = 0;
   int          lastKernel = 0;           // DPCU_KERNEL_* of the last cull launched (DPCU_CULL_OPT_LAST_KERNEL)
   uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
@@ -168,6 +170,29 @@ namespace dpcu
       DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );
       ctx->maxIndexKnown = true;
     }
+    return DPCU_OK;
+  }
+
+  // every object's transform index must address a matrix (the reference would read out of bounds); the running
+  // maximum is exact until objects are overwritten or removed, then it is recomputed before it may reject a cull
+  static int checkIndexRange( dpcuCull *ctx, char const *who )
+  {
+    if ( !ctx->n ) return DPCU_OK;
+    DPCU_TRY( refreshMaxIndex( ctx ) );
+    if ( ctx->maxTransformIndex >= ctx->nMats && ctx->maxIndexStale )
+    {
+      DPCU_CUDA( cudaMemsetAsync( ctx->maxIndex.ptr, 0, 4, ctx->stream ) );
+      int grid = int( divUp( ctx->n, 256 ) );
+      if ( grid > ctx->smCount * 8 ) grid = ctx->smCount * 8;
+      maxIndexKernel<<<grid, 256, 0, ctx->stream>>>( static_cast<float4 const *>( ctx->lowerIdx.ptr ), uint32_t( ctx->n ), static_cast<uint32_t *>( ctx->maxIndex.ptr ) );
+      DPCU_CUDA( cudaGetLastError() );
+      ++ctx->launches;
+      ctx->maxIndexKnown = false;
+      ctx->maxIndexStale = false;
+      DPCU_TRY( refreshMaxIndex( ctx ) );
+    }
+    if ( ctx->maxTransformIndex >= ctx->nMats )
+      return fail( DPCU_ERR_INVALID_VALUE, "%s: transform index %u out of range (%zu matrices)", who, ctx->maxTransformIndex, ctx->nMats );
     return DPCU_OK;
   }
 
@@ -537,6 +562,7 @@ extern "C"
     cudaStreamSynchronize( ctx->stream );
     ctx->lowerIdx.release(); ctx->extent.release(); ctx->mats.release(); ctx->scratch.release(); ctx->maxIndex.release();
     ctx->staging.release();
+    ctx->stagingFree.destroy();
     ctx->uploads.destroy();
     ctx->lastRun.hostWait();
     ctx->lastRun.destroy();
@@ -591,6 +617,7 @@ extern "C"
   int dpcuCullSetObjects( dpcuCull *ctx, const float *lower4, const float *extent4, const uint32_t *transformIndex,
                           size_t n, int memspace )
   {
+    dpcu::Range nvtxRange( "dpcuCullSetObjects" );
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     DPCU_REQUIRE( n < ( size_t( 1 ) << 32 ), "object count must fit 32 bits" );
     DPCU_REQUIRE( memspace == DPCU_MEM_HOST || memspace == DPCU_MEM_DEVICE, "bad memspace" );
@@ -605,6 +632,56 @@ extern "C"
     return dpcuCullSetObjectRange( ctx, 0, n, lower4, extent4, transformIndex, memspace );
   }
 
+  int dpcuCullSetObjectCount( dpcuCull *ctx, size_t n )
+  {
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( n < ( size_t( 1 ) << 32 ), "object count must fit 32 bits" );
+    if ( n == ctx->n ) return DPCU_OK;
+    dpcu::DeviceGuard guard( ctx->device );
+    DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
+    DPCU_TRY( ctx->lowerIdx.reserve( ( n ? n : 1 ) * 16, true, ctx->stream ) );
+    DPCU_TRY( ctx->extent.reserve( ( n ? n : 1 ) * 16, true, ctx->stream ) );
+    if ( n < ctx->n ) ctx->maxIndexStale = true;
+    ctx->n = n;
+    ++ctx->objectsVersion;
+    return DPCU_OK;
+  }
+
+  int dpcuCullUpdateObjects( dpcuCull *ctx, const uint32_t *indices, size_t k, const float *lower4, const float *extent4,
+                             const uint32_t *transformIndex )
+  {
+    dpcu::Range nvtxRange( "dpcuCullUpdateObjects" );
+    DPCU_REQUIRE( ctx, "ctx is NULL" );
+    DPCU_REQUIRE( !k || ( indices && lower4 && extent4 && transformIndex ), "NULL argument" );
+    DPCU_REQUIRE( k < ( size_t( 1 ) << 32 ), "batch must fit 32 bits" );
+    if ( !k ) return DPCU_OK;
+    dpcu::DeviceGuard guard( ctx->device );
+    DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
+    // [lower | extent | tidx | indices] through the pinned staging buffer: one copy, one kernel, and the caller does not
+    // wait for either - the NEXT user of the staging buffer does
+    ctx->stagingFree.hostWait();
+    DPCU_TRY( ctx->staging.reserve( k * 40 ) );
+    char *st = static_cast<char *>( ctx->staging.ptr );
+    memcpy( st, lower4, k * 16 );
+    memcpy( st + k * 16, extent4, k * 16 );
+    memcpy( st + k * 32, transformIndex, k * 4 );
+    memcpy( st + k * 36, indices, k * 4 );
+    DPCU_TRY( ctx->scratch.reserve( k * 40, false, ctx->stream ) );
+    char *d = static_cast<char *>( ctx->scratch.ptr );
+    DPCU_CUDA( cudaMemcpyAsync( d, st, k * 40, cudaMemcpyHostToDevice, ctx->stream ) );
+    DPCU_CUDA( ctx->stagingFree.record( ctx->stream ) );
+    dpcu::scatterObjectsKernel<<<unsigned( dpcu::divUp( k, 256 ) ), 256, 0, ctx->stream>>>(
+      reinterpret_cast<uint32_t const *>( d + k * 36 ), reinterpret_cast<float4 const *>( d ), reinterpret_cast<float4 const *>( d + k * 16 ),
+      reinterpret_cast<uint32_t const *>( d + k * 32 ), uint32_t( k ), uint32_t( ctx->n ), static_cast<float4 *>( ctx->lowerIdx.ptr ),
+      static_cast<float4 *>( ctx->extent.ptr ), static_cast<uint32_t *>( ctx->maxIndex.ptr ) );
+    DPCU_CUDA( cudaGetLastError() );
+    ++ctx->launches;
+    ++ctx->objectsVersion;
+    ctx->maxIndexKnown = false;
+    ctx->maxIndexStale = true;
+    return DPCU_OK;
+  }
+
   int dpcuCullGetObjectCount( const dpcuCull *ctx, size_t *n )
   {
     DPCU_REQUIRE( ctx && n, "NULL argument" );
@@ -614,6 +691,7 @@ extern "C"
 
   int dpcuCullSetMatrices( dpcuCull *ctx, const void *matrices, size_t count, size_t strideBytes, int memspace )
   {
+    dpcu::Range nvtxRange( "dpcuCullSetMatrices" );
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     DPCU_REQUIRE( !count || matrices, "matrices is NULL" );
     DPCU_REQUIRE( strideBytes >= 64 && strideBytes % 4 == 0, "stride must be >= 64 and a multiple of 4" );
@@ -645,6 +723,7 @@ extern "C"
   int dpcuCullUpdateMatrices( dpcuCull *ctx, const uint32_t *indices, size_t n, const void *matrices, size_t strideBytes,
                               int memspace )
   {
+    dpcu::Range nvtxRange( "dpcuCullUpdateMatrices" );
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     DPCU_REQUIRE( !n || ( indices && matrices ), "NULL argument" );
     DPCU_REQUIRE( strideBytes >= 64 && strideBytes % 4 == 0, "stride must be >= 64 and a multiple of 4" );
@@ -655,6 +734,7 @@ extern "C"
     DPCU_CUDA( ctx->lastRun.orderBefore( ctx->stream ) );
     // pack [matrices | indices] into pinned staging, skipping indices past the matrix count
     // (markMatrixDirty ignores those, dp/culling/GroupBitSet.h:140-150)
+    ctx->stagingFree.hostWait();
     DPCU_TRY( ctx->staging.reserve( n * 68 ) );
     char *st = static_cast<char *>( ctx->staging.ptr );
     uint32_t *sidx = reinterpret_cast<uint32_t *>( st + n * 64 );
@@ -676,7 +756,7 @@ extern "C"
       static_cast<float4 const *>( ctx->scratch.ptr ), uint32_t( k ), static_cast<float4 *>( ctx->mats.ptr ) );
     DPCU_CUDA( cudaGetLastError() );
     ++ctx->launches;
-    DPCU_CUDA( cudaStreamSynchronize( ctx->stream ) );   // staging is reused by the next call
+    DPCU_CUDA( ctx->stagingFree.record( ctx->stream ) );  // the next user of the staging buffer waits for this, the caller does not
     return DPCU_OK;
   }
 
@@ -767,13 +847,7 @@ extern "C"
       DPCU_CUDA( ctx->uploads.orderBefore( s ) );
     }
     const size_t n = ctx->n;
-    if ( n )
-    {
-      DPCU_TRY( dpcu::refreshMaxIndex( ctx ) );
-      if ( ctx->maxTransformIndex >= ctx->nMats )
-        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullRun: transform index %u out of range (%zu matrices)",
-                           ctx->maxTransformIndex, ctx->nMats );
-    }
+    DPCU_TRY( dpcu::checkIndexRange( ctx, "dpcuCullRun" ) );
     for ( int v = 0; v < nViews; ++v )
     {
       dpcuCullResult *r = results[v];
@@ -907,6 +981,7 @@ extern "C"
 {
   int dpcuCullRun( dpcuCull *ctx, dpcuCullResult *const *results, const float *viewProjections, int nViews, dpcuStream *stream )
   {
+    dpcu::Range nvtxRange( "dpcuCullRun" );
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     dpcu::DeviceGuard guard( ctx->device );
     cudaStream_t s = stream ? stream->stream : ctx->stream;
@@ -917,6 +992,7 @@ extern "C"
   int dpcuCullRunWithTree( dpcuCull *ctx, dpcuTree *tree, dpcuCullResult *const *results, const float *viewProjections, int nViews,
                            dpcuStream *stream )
   {
+    dpcu::Range nvtxRange( "dpcuCullRunWithTree" );
     DPCU_REQUIRE( ctx && tree, "NULL argument" );
     DPCU_REQUIRE( tree->device == ctx->device, "tree and culling context live on different devices" );
     DPCU_REQUIRE( tree->numNodes >= 1, "no topology set" );
@@ -1061,6 +1137,34 @@ extern "C"
     return DPCU_OK;
   }
 
+  int dpcuCullResultUpdateWords( dpcuCullResult *r, const uint32_t *indices, const uint32_t *words, size_t k )
+  {
+    DPCU_REQUIRE( r, "result is NULL" );
+    DPCU_REQUIRE( !k || ( indices && words ), "NULL argument" );
+    if ( !k ) return DPCU_OK;
+    const size_t have = dpcu::divUp( r->n, 32 );
+    for ( size_t i = 0; i < k; ++i ) DPCU_REQUIRE( indices[i] < have, "word index beyond the stored result" );
+    dpcuCull *ctx = r->ctx;
+    dpcu::DeviceGuard guard( ctx->device );
+    cudaStream_t s = ctx->stream;
+    DPCU_CUDA( r->done.orderBefore( s ) );
+    ctx->stagingFree.hostWait();
+    DPCU_TRY( ctx->staging.reserve( k * 8 ) );
+    char *st = static_cast<char *>( ctx->staging.ptr );
+    memcpy( st, indices, k * 4 );
+    memcpy( st + k * 4, words, k * 4 );
+    DPCU_TRY( ctx->scratch.reserve( k * 8, false, s ) );
+    DPCU_CUDA( cudaMemcpyAsync( ctx->scratch.ptr, st, k * 8, cudaMemcpyHostToDevice, s ) );
+    DPCU_CUDA( ctx->stagingFree.record( s ) );
+    dpcu::scatterWordsKernel<<<unsigned( dpcu::divUp( k, 256 ) ), 256, 0, s>>>( static_cast<uint32_t const *>( ctx->scratch.ptr ),
+      static_cast<uint32_t const *>( ctx->scratch.ptr ) + k, uint32_t( k ), static_cast<uint32_t *>( r->bits.ptr ), r->ran ? r->dBits : nullptr );
+    DPCU_CUDA( cudaGetLastError() );
+    DPCU_CUDA( r->done.record( s ) );
+    ++ctx->launches;
+    r->visBuilt = false;
+    return DPCU_OK;
+  }
+
   int dpcuCullResultDevicePointers( dpcuCullResult *r, const uint32_t **bits, size_t *nWords, const uint32_t **changedIndices,
                                     const uint32_t **changedCount )
   {
@@ -1086,6 +1190,7 @@ extern "C"
 
   int dpcuCullResultBuildVisibleList( dpcuCullResult *r, dpcuStream *stream )
   {
+    dpcu::Range nvtxRange( "dpcuCullResultBuildVisibleList" );
     DPCU_REQUIRE( r, "result is NULL" );
     dpcuCull *ctx = r->ctx;
     dpcu::DeviceGuard guard( ctx->device );
@@ -1193,6 +1298,7 @@ extern "C"
 
   int dpcuCullResultSynchronize( dpcuCullResult *r )
   {
+    dpcu::Range nvtxRange( "dpcuCullResultSynchronize" );
     DPCU_REQUIRE( r, "result is NULL" );
     dpcu::DeviceGuard guard( r->ctx->device );
     if ( r->done.pending ) DPCU_CUDA( cudaEventSynchronize( r->done.event ) );
@@ -1201,16 +1307,14 @@ extern "C"
 
   int dpcuCullGetBoundingBox( dpcuCull *ctx, float *out6 )
   {
+    dpcu::Range nvtxRange( "dpcuCullGetBoundingBox" );
     DPCU_REQUIRE( ctx && out6, "NULL argument" );
     dpcu::DeviceGuard guard( ctx->device );
     const float FMAX = 3.402823466e+38f;
     float lo[3] = { FMAX, FMAX, FMAX }, hi[3] = { -FMAX, -FMAX, -FMAX };
     if ( ctx->n )
     {
-      DPCU_TRY( dpcu::refreshMaxIndex( ctx ) );
-      if ( ctx->maxTransformIndex >= ctx->nMats )
-        return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetBoundingBox: transform index %u out of range (%zu matrices)",
-                           ctx->maxTransformIndex, ctx->nMats );
+      DPCU_TRY( dpcu::checkIndexRange( ctx, "dpcuCullGetBoundingBox" ) );
       DPCU_TRY( ctx->scratch.reserve( 256, false, ctx->stream ) );
       uint32_t init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
       DPCU_CUDA( cudaMemcpyAsync( ctx->scratch.ptr, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream ) );

@@ -10,6 +10,11 @@
 
 #include "../../include/dpcu.h"
 
+// NVTX ranges around the entry points of the hot path (the reference brackets the same places
+// with dp::util::ProfileEntry, dp/culling/cpu/src/ManagerImpl.cpp:469, dp/sg/xbar/src/SceneTree.cpp:157).  Header-only
+// NVTX v3: without a profiler attached a range is one predictable branch.
+#include <nvtx3/nvToolsExt.h>
+
 namespace dpcu
 {
   // thread-local message behind dpcuGetLastError()
@@ -19,6 +24,14 @@ namespace dpcu
 
   // fails loudly when no device is usable: there is no CPU fallback anywhere in this library
   int   requireDevice();
+
+  struct Range
+  {
+    explicit Range( char const *name ) { nvtxRangePushA( name ); }
+    ~Range() { nvtxRangePop(); }
+    Range( Range const & ) = delete;
+    Range & operator=( Range const & ) = delete;
+  };
 
   struct DeviceGuard
   {

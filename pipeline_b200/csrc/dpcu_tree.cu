@@ -129,6 +129,46 @@ namespace dpcu
   // Tree::compute in three steps so that the culling layer can run the last level inside its own
   // kernel (dpcuCullRunWithTree): begin = ordering + drop the previous published dirty set,
   // levels [first, last), end = clear the local dirty bits (Tree.cpp:163) + fence.
+  // world matrices of the nodes whose dirty-world bit is set, compacted (order irrelevant: every matrix travels with its
+  // node index) - what dp::transform::cuda::Tree needs to refresh the host copy behind getWorldMatrices()
+  __global__ void __launch_bounds__( 256 ) gatherDirtyWorldKernel( uint32_t const *dirtyWorld, float4 const *world, uint32_t nWords,
+                                                                   uint32_t capacity, uint32_t *counter, uint32_t *outIndex, float4 *outMats )
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    for ( uint32_t w0 = ( blockIdx.x * blockDim.x + threadIdx.x ) & ~31u; w0 < nWords; w0 += gridDim.x * blockDim.x )
+    {
+      const uint32_t w = w0 + lane;
+      uint32_t bits = w < nWords ? dirtyWorld[w] : 0u;
+      const uint32_t pc = __popc( bits );
+      uint32_t incl = pc;
+#pragma unroll
+      for ( int d = 1; d < 32; d <<= 1 )
+      {
+        const uint32_t t = __shfl_up_sync( 0xffffffffu, incl, d );
+        if ( lane >= d ) incl += t;
+      }
+      const uint32_t total = __shfl_sync( 0xffffffffu, incl, 31 );
+      if ( !total ) continue;
+      uint32_t base = 0;
+      if ( lane == 0 ) base = atomicAdd( counter, total );
+      base = __shfl_sync( 0xffffffffu, base, 0 );
+      uint32_t slot = base + incl - pc;
+      while ( bits )
+      {
+        const uint32_t node = ( w << 5 ) + uint32_t( __ffs( bits ) - 1 );
+        bits &= bits - 1;
+        if ( slot < capacity )
+        {
+          outIndex[slot] = node;
+          float4 const *m = world + 4ull * node;
+          float4 *o = outMats + 4ull * slot;
+          o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[3];
+        }
+        ++slot;
+      }
+    }
+  }
+
   int treeBeginCompute( dpcuTree *t, cudaStream_t s )
   {
     if ( s != t->stream )
@@ -214,6 +254,8 @@ extern "C"
     t->done.destroy();
     t->uploads.destroy();
     t->readers.destroy();
+    t->gather.release();
+    t->gatherHost.release();
     t->local.release(); t->world.release(); t->entries.release(); t->dirtyLocal.release(); t->dirtyWorld.release(); t->scratch.release();
     cudaStreamDestroy( t->stream );
     delete t;
@@ -222,6 +264,7 @@ extern "C"
 
   int dpcuTreeSetTopology( dpcuTree *t, const uint32_t *entries, const uint32_t *levelOffsets, int numLevels, size_t numNodes )
   {
+    dpcu::Range nvtxRange( "dpcuTreeSetTopology" );
     DPCU_REQUIRE( t, "tree is NULL" );
     DPCU_REQUIRE( numLevels >= 0 && ( numLevels == 0 || ( entries && levelOffsets ) ), "NULL topology" );
     DPCU_REQUIRE( numNodes >= 1 && numNodes < ( size_t( 1 ) << 30 ), "numNodes must be in [1, 2^30)" );
@@ -289,6 +332,7 @@ extern "C"
 
   int dpcuTreeSetLocals( dpcuTree *t, size_t first, size_t count, const float *matrices, int memspace )
   {
+    dpcu::Range nvtxRange( "dpcuTreeSetLocals" );
     DPCU_REQUIRE( t, "tree is NULL" );
     DPCU_REQUIRE( first + count <= t->numNodes, "range exceeds node count" );
     DPCU_REQUIRE( matrices || !count, "matrices is NULL" );
@@ -305,6 +349,7 @@ extern "C"
 
   int dpcuTreeUpdateLocals( dpcuTree *t, const uint32_t *indices, size_t n, const float *matrices, int memspace )
   {
+    dpcu::Range nvtxRange( "dpcuTreeUpdateLocals" );
     DPCU_REQUIRE( t, "tree is NULL" );
     DPCU_REQUIRE( !n || ( indices && matrices ), "NULL argument" );
     DPCU_REQUIRE( memspace == DPCU_MEM_HOST, "scattered updates take host memory (indices and matrices)" );
@@ -328,6 +373,7 @@ extern "C"
 
   int dpcuTreeCompute( dpcuTree *t, dpcuStream *stream )
   {
+    dpcu::Range nvtxRange( "dpcuTreeCompute" );
     DPCU_REQUIRE( t, "tree is NULL" );
     DPCU_REQUIRE( t->numNodes >= 1, "no topology set" );
     dpcu::DeviceGuard guard( t->device );
@@ -377,6 +423,59 @@ extern "C"
     DPCU_CUDA( cudaMemcpyAsync( hostWords, t->dirtyWorld.ptr, have * 4, cudaMemcpyDeviceToHost, t->stream ) );
     DPCU_CUDA( cudaStreamSynchronize( t->stream ) );
     return DPCU_OK;
+  }
+
+  int dpcuTreeGetWorldDirty( dpcuTree *t, float *hostWorld, size_t numNodes, size_t *updated )
+  {
+    dpcu::Range nvtxRange( "dpcuTreeGetWorldDirty" );
+    DPCU_REQUIRE( t && hostWorld, "NULL argument" );
+    DPCU_REQUIRE( numNodes >= t->numNodes, "hostWorld holds fewer matrices than the tree has nodes" );
+    if ( updated ) *updated = 0;
+    if ( !t->numNodes ) return DPCU_OK;
+    dpcu::DeviceGuard guard( t->device );
+    cudaStream_t s = t->stream;
+    DPCU_CUDA( t->done.orderBefore( s ) );
+    const size_t nWords = dpcu::divUp( t->numNodes, 32 );
+    // first a count (one word back), then exactly that many {index, matrix} records through pinned staging
+    DPCU_TRY( t->scratch.reserve( 256, false, s ) );
+    uint32_t *counter = static_cast<uint32_t *>( t->scratch.ptr );
+    // capacity grows with the dirty set: gather into what is there (the kernel counts everything, stores what fits), and
+    // if it did not fit, size for the count and run once more
+    for ( int attempt = 0; attempt < 2; ++attempt )
+    {
+      const size_t cap = t->gather.capacity / 72;
+      DPCU_CUDA( cudaMemsetAsync( counter, 0, 4, s ) );
+      unsigned grid = unsigned( dpcu::divUp( nWords, 256 ) );
+      if ( grid > unsigned( t->smCount ) * 8u ) grid = unsigned( t->smCount ) * 8u;
+      uint32_t *outIndex = static_cast<uint32_t *>( t->gather.ptr );
+      float4 *outMats = reinterpret_cast<float4 *>( static_cast<char *>( t->gather.ptr ) + ( ( cap * 4 + 255 ) & ~size_t( 255 ) ) );
+      dpcu::gatherDirtyWorldKernel<<<grid, 256, 0, s>>>( static_cast<uint32_t const *>( t->dirtyWorld.ptr ), static_cast<float4 const *>( t->world.ptr ),
+                                                         uint32_t( nWords ), uint32_t( cap ), counter, outIndex, outMats );
+      DPCU_CUDA( cudaGetLastError() );
+      ++t->launches;
+      uint32_t count = 0;
+      DPCU_CUDA( cudaMemcpyAsync( &count, counter, 4, cudaMemcpyDeviceToHost, s ) );
+      DPCU_CUDA( cudaStreamSynchronize( s ) );
+      if ( count <= cap )
+      {
+        if ( count )
+        {
+          DPCU_TRY( t->gatherHost.reserve( size_t( count ) * 68 ) );
+          uint32_t *hIndex = static_cast<uint32_t *>( t->gatherHost.ptr );
+          float *hMats = reinterpret_cast<float *>( static_cast<char *>( t->gatherHost.ptr ) + size_t( count ) * 4 );
+          DPCU_CUDA( cudaMemcpyAsync( hIndex, outIndex, size_t( count ) * 4, cudaMemcpyDeviceToHost, s ) );
+          DPCU_CUDA( cudaMemcpyAsync( hMats, outMats, size_t( count ) * 64, cudaMemcpyDeviceToHost, s ) );
+          DPCU_CUDA( cudaStreamSynchronize( s ) );
+          for ( uint32_t k = 0; k < count; ++k ) memcpy( hostWorld + 16ull * hIndex[k], hMats + 16ull * k, 64 );
+        }
+        if ( updated ) *updated = count;
+        return DPCU_OK;
+      }
+      size_t want = size_t( count ) + count / 4 + 64;
+      if ( want > t->numNodes ) want = t->numNodes;
+      DPCU_TRY( t->gather.reserve( want * 72 + 512, false, s ) );
+    }
+    return dpcu::fail( DPCU_ERR_NOT_READY, "dpcuTreeGetWorldDirty: the dirty set changed while it was being gathered" );
   }
 
   int dpcuTreeSetOption( dpcuTree *t, int option, size_t value )

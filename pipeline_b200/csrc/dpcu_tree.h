@@ -11,6 +11,8 @@ struct dpcuTree
   int          device = 0;
   cudaStream_t stream = nullptr;
   dpcu::DeviceArray local, world, entries, dirtyLocal, dirtyWorld, scratch;
+  dpcu::DeviceArray gather;      // dpcuTreeGetWorldDirty: compacted {node index, world matrix} records
+  dpcu::PinnedArray gatherHost;
   size_t       numNodes = 0;
   size_t       numEntries = 0;
   std::vector<uint32_t> levelOffsets;

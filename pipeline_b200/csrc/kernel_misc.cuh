@@ -124,6 +124,45 @@ namespace dpcu
     if ( ( threadIdx.x & 31 ) == 0 && m ) atomicMax( maxIndex, m );
   }
 
+  // batched edit of live objects (objectSetBoundingBox / objectSetTransformIndex, swap-removes, appends):
+  // object indices[k] <- (lower[k], extent[k], tidx[k]); indices past the object count are skipped
+  __global__ void scatterObjectsKernel( uint32_t const *indices, float4 const *lower, float4 const *extent, uint32_t const *tidx, uint32_t k,
+                                        uint32_t n, float4 *lowerIdx, float4 *extentOut, uint32_t *maxIndex )
+  {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;
+    if ( t < k )
+    {
+      const uint32_t i = indices[t];
+      if ( i < n )
+      {
+        float4 lo = lower[t];
+        float4 ex = extent[t];
+        lo.w = __uint_as_float( tidx[t] );
+        ex.w = 0.0f;
+        lowerIdx[i]  = lo;
+        extentOut[i] = ex;
+        m = tidx[t];
+      }
+    }
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 ) m = max( m, __shfl_xor_sync( 0xffffffffu, m, d ) );
+    if ( ( threadIdx.x & 31 ) == 0 && m ) atomicMax( maxIndex, m );
+  }
+
+  // exact largest transform index of the current objects (after overwrites / removals the running maximum may be stale)
+  __global__ void maxIndexKernel( float4 const *lowerIdx, uint32_t n, uint32_t *maxIndex )
+  {
+    uint32_t m = 0;
+    for ( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+    {
+      m = max( m, __ldg( reinterpret_cast<uint32_t const *>( lowerIdx + i ) + 3 ) );
+    }
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 ) m = max( m, __shfl_xor_sync( 0xffffffffu, m, d ) );
+    if ( ( threadIdx.x & 31 ) == 0 && m ) atomicMax( maxIndex, m );
+  }
+
   // matrices[indices[k]] = packed[k]
   __global__ void scatterMatricesKernel( uint32_t const *indices, float4 const *packed, uint32_t n, float4 *mats )
   {
@@ -164,6 +203,17 @@ namespace dpcu
       w = value ? ( w | ( 1u << ( newIndex & 31 ) ) ) : ( w & ~( 1u << ( newIndex & 31 ) ) );
       bits[newIndex >> 5] = w;
       if ( mirror ) mirror[newIndex >> 5] = w;
+    }
+  }
+
+  // a frame's bit moves applied on the host mirror, the touched words written back in one batch
+  __global__ void scatterWordsKernel( uint32_t const *indices, uint32_t const *words, uint32_t k, uint32_t *bits, uint32_t *mirror )
+  {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( t < k )
+    {
+      bits[indices[t]] = words[t];
+      if ( mirror ) mirror[indices[t]] = words[t];
     }
   }
 

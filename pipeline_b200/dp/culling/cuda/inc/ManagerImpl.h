@@ -46,7 +46,8 @@ namespace dp
         void const *          m_deviceMatrices;       // non-null: borrowed device array is bound
         size_t                m_deviceMatricesCount;
         bool                  m_deviceMatricesBound;
-        std::vector<uint32_t> m_editedObjects;        // live objects whose box / index changed since the last update
+        size_t                m_deviceObjects;        // objects on the device (~0: never uploaded)
+        std::vector<uint32_t> m_editedObjects;        // group indices touched by adds / removes / live edits since the last update
         std::vector<float>    m_stageLower, m_stageExtent;
         std::vector<uint32_t> m_stageIndex;
       };
@@ -61,6 +62,8 @@ namespace dp
 
         /** \brief Size the pinned host mirror for the group's current object count; call before the cull is queued. **/
         void prepare();
+        /** \brief Bit moves of removed objects were applied on the host mirror: write the touched words back to the device. **/
+        void flushMovedBits();
         /** \brief Wait for the cull that was just queued; its bitset and changed list are in the host mirror then. **/
         void fetch();
 
@@ -89,6 +92,8 @@ namespace dp
         uint32_t *                   m_changedCount;
         size_t                       m_capacity;        // objects the mirror has room for
         size_t                       m_size;
+        std::vector<uint32_t>        m_touchedWords;    // words of m_bits edited by onNotify since the last flush
+        std::vector<uint32_t>        m_touchedValues;
       };
 
       class ManagerImpl : public Manager
@@ -103,6 +108,7 @@ namespace dp
 
         virtual GroupSharedPtr groupCreate();
         virtual void groupAddObject( GroupSharedPtr const & group, ObjectSharedPtr const & object );
+        virtual void groupRemoveObject( GroupSharedPtr const & group, ObjectSharedPtr const & object );
         virtual ResultSharedPtr groupCreateResult( GroupSharedPtr const & group );
         virtual void groupSetDeviceMatrices( GroupSharedPtr const & group, void const * deviceMatrices, size_t numberOfMatrices );
 

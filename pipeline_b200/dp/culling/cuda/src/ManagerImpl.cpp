@@ -10,6 +10,7 @@
 #include <dp/culling/cuda/inc/ManagerImpl.h>
 #include <dp/util/FrameProfiler.h>
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 
@@ -44,6 +45,7 @@ namespace dp
         , m_deviceMatrices( nullptr )
         , m_deviceMatricesCount( 0 )
         , m_deviceMatricesBound( false )
+        , m_deviceObjects( ~size_t( 0 ) )
       {
         DPCU_VERIFY( dpcuCullCreate( &m_ctx, device ) );
       }
@@ -69,39 +71,43 @@ namespace dp
 
       void GroupCUDA::update()
       {
-        // ---- objects: whole array after add / remove (GroupBitSet.cpp:76-119 set m_inputChanged) ...
-        if ( m_inputChanged )
+        // ---- objects.  Every add, remove (GroupBitSet.cpp:93-119: the last object moves into the freed slot) and live
+        // edit since the last update marked the group indices it touched; they go to the device as ONE batch
+        // (dpcuCullSetObjectCount keeps what is there, dpcuCullUpdateObjects scatters the touched objects).  Only a group
+        // that was never uploaded, or one in which more than a quarter of the objects changed, is uploaded whole.
+        size_t const n = getObjectCount();
+        if ( m_inputChanged || !m_editedObjects.empty() )
         {
           dp::util::ProfileEntry p( "cull::updateInputBuffer" );
-          size_t const n = getObjectCount();
-          m_stageLower.resize( 4 * n );
-          m_stageExtent.resize( 4 * n );
-          m_stageIndex.resize( n );
-          for ( size_t index = 0; index < n; ++index )
+          std::sort( m_editedObjects.begin(), m_editedObjects.end() );
+          m_editedObjects.erase( std::unique( m_editedObjects.begin(), m_editedObjects.end() ), m_editedObjects.end() );
+          while ( !m_editedObjects.empty() && m_editedObjects.back() >= n )
           {
-            ObjectBitSetSharedPtr const & object = getObject( index );
-            memcpy( &m_stageLower[4 * index], object->getLowerLeft().getPtr(), 4 * sizeof(float) );
-            memcpy( &m_stageExtent[4 * index], object->getExtent().getPtr(), 4 * sizeof(float) );
-            m_stageIndex[index] = static_cast<uint32_t>( object->getTransformIndex() );
+            m_editedObjects.pop_back();     // indices that a later remove took away again
           }
-          DPCU_VERIFY( dpcuCullSetObjects( m_ctx, m_stageLower.data(), m_stageExtent.data(), m_stageIndex.data(), n, DPCU_MEM_HOST ) );
+          bool const whole = m_deviceObjects == ~size_t( 0 ) || 4 * m_editedObjects.size() > n;
+          size_t const count = whole ? n : m_editedObjects.size();
+          m_stageLower.resize( 4 * count );
+          m_stageExtent.resize( 4 * count );
+          m_stageIndex.resize( count );
+          for ( size_t k = 0; k < count; ++k )
+          {
+            ObjectBitSetSharedPtr const & object = getObject( whole ? k : m_editedObjects[k] );
+            memcpy( &m_stageLower[4 * k], object->getLowerLeft().getPtr(), 4 * sizeof(float) );
+            memcpy( &m_stageExtent[4 * k], object->getExtent().getPtr(), 4 * sizeof(float) );
+            m_stageIndex[k] = static_cast<uint32_t>( object->getTransformIndex() );
+          }
+          if ( whole )
+          {
+            DPCU_VERIFY( dpcuCullSetObjects( m_ctx, m_stageLower.data(), m_stageExtent.data(), m_stageIndex.data(), n, DPCU_MEM_HOST ) );
+          }
+          else
+          {
+            DPCU_VERIFY( dpcuCullSetObjectCount( m_ctx, n ) );
+            DPCU_VERIFY( dpcuCullUpdateObjects( m_ctx, m_editedObjects.data(), count, m_stageLower.data(), m_stageExtent.data(), m_stageIndex.data() ) );
+          }
+          m_deviceObjects = n;
           m_inputChanged = false;
-          m_editedObjects.clear();
-        }
-        // ---- ... or just the live objects that were edited (objectSetBoundingBox / objectSetTransformIndex)
-        else if ( !m_editedObjects.empty() )
-        {
-          for ( size_t i = 0; i < m_editedObjects.size(); ++i )
-          {
-            size_t const index = m_editedObjects[i];
-            if ( index < getObjectCount() )
-            {
-              ObjectBitSetSharedPtr const & object = getObject( index );
-              uint32_t transformIndex = static_cast<uint32_t>( object->getTransformIndex() );
-              DPCU_VERIFY( dpcuCullSetObjectRange( m_ctx, index, 1, object->getLowerLeft().getPtr(), object->getExtent().getPtr()
-                                                 , &transformIndex, DPCU_MEM_HOST ) );
-            }
-          }
           m_editedObjects.clear();
         }
 
@@ -177,8 +183,27 @@ namespace dp
         dpcuHostBufferDestroy( m_mirrorCount );
       }
 
+      void ResultCUDA::flushMovedBits()
+      {
+        if ( m_touchedWords.empty() )
+        {
+          return;
+        }
+        std::sort( m_touchedWords.begin(), m_touchedWords.end() );
+        m_touchedWords.erase( std::unique( m_touchedWords.begin(), m_touchedWords.end() ), m_touchedWords.end() );
+        m_touchedValues.resize( m_touchedWords.size() );
+        for ( size_t k = 0; k < m_touchedWords.size(); ++k )
+        {
+          m_touchedValues[k] = m_bits[m_touchedWords[k]];
+        }
+        DPCU_VERIFY( dpcuCullResultUpdateWords( m_result, m_touchedWords.data(), m_touchedValues.data(), m_touchedWords.size() ) );
+        DPCU_VERIFY( dpcuCullResultSynchronize( m_result ) );   // the kernel also stores into the mirror: let it finish before the host edits again
+        m_touchedWords.clear();
+      }
+
       void ResultCUDA::prepare()
       {
+        flushMovedBits();
         size_t const count = m_groupParent->getObjectCount();
         if ( count <= m_capacity && m_mirrorBits )
         {
@@ -241,11 +266,26 @@ namespace dp
 
       void ResultCUDA::onNotify( dp::util::Event const & event, dp::util::Payload * /*payload*/ )
       {
-        // ResultBitSet::onNotify, dp/culling/src/ResultBitSet.cpp:110-128: the bit moves on the device, the same
-        // kernel stores the touched word into the host mirror; removal is not on the hot path, so wait for it
+        // ResultBitSet::onNotify, dp/culling/src/ResultBitSet.cpp:110-128
         GroupBitSet::Event const & groupEvent = static_cast<GroupBitSet::Event const &>( event );
-        DPCU_VERIFY( dpcuCullResultMoveBit( m_result, groupEvent.getOldIndex(), groupEvent.getNewIndex() ) );
-        DPCU_VERIFY( dpcuCullResultSynchronize( m_result ) );
+        size_t const oldIndex = groupEvent.getOldIndex(), newIndex = groupEvent.getNewIndex();
+        if ( m_bits && m_size )
+        {
+          // the host mirror holds the bits of the last cull: move the bit there (same rule as the device kernel) and
+          // remember the word; all words a frame's removals touched go back to the device in one batch before the next cull
+          if ( newIndex < m_size )
+          {
+            uint32_t const value = ( oldIndex < m_size ) ? ( ( m_bits[oldIndex >> 5] >> ( oldIndex & 31 ) ) & 1u ) : 1u;
+            uint32_t & word = m_bits[newIndex >> 5];
+            word = value ? ( word | ( 1u << ( newIndex & 31 ) ) ) : ( word & ~( 1u << ( newIndex & 31 ) ) );
+            m_touchedWords.push_back( static_cast<uint32_t>( newIndex >> 5 ) );
+          }
+        }
+        else
+        {
+          DPCU_VERIFY( dpcuCullResultMoveBit( m_result, oldIndex, newIndex ) );
+          DPCU_VERIFY( dpcuCullResultSynchronize( m_result ) );
+        }
       }
 
       void ResultCUDA::onDestroyed( dp::util::Subject const & /*subject*/, dp::util::Payload * /*payload*/ )
@@ -287,7 +327,17 @@ namespace dp
         ManagerBitSet::groupAddObject( group, object );
         // The reference never connects an object to its group (hard part 5); this
         // backend does, so that edits of live objects reach the device mirror.
-        std::static_pointer_cast<ObjectBitSet>( object )->setGroup( std::static_pointer_cast<GroupBitSet>( group ) );
+        ObjectBitSetSharedPtr objectImpl = std::static_pointer_cast<ObjectBitSet>( object );
+        objectImpl->setGroup( std::static_pointer_cast<GroupBitSet>( group ) );
+        std::static_pointer_cast<GroupCUDA>( group )->markObjectEdited( objectImpl->getGroupIndex() );   // the new slot
+      }
+
+      void ManagerImpl::groupRemoveObject( GroupSharedPtr const & group, ObjectSharedPtr const & object )
+      {
+        size_t const freed = std::static_pointer_cast<ObjectBitSet>( object )->getGroupIndex();
+        ManagerBitSet::groupRemoveObject( group, object );      // throws if the object is not in this group
+        // the last object now lives in the freed slot (GroupBitSet.cpp:98-105): that slot is what changed on the device
+        std::static_pointer_cast<GroupCUDA>( group )->markObjectEdited( freed );
       }
 
       void ManagerImpl::objectSetBoundingBox( ObjectSharedPtr const & object, dp::math::Box3f const & boundingBox )

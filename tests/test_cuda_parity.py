@@ -336,7 +336,14 @@ def test_fma_mode_reports_disagreements(capi, port):
     ctx = capi.Cull(0)
     ctx.set_objects(lower4, extent4, tidx)
     ctx.set_matrices(mats.reshape(-1))
-    vp = scenes.camera_c2()
+    total = 0
+    for vp in (scenes.camera_c2(), scenes.orbit_camera(3), scenes.orbit_camera(11), scenes.cube_map_cameras((40.0, -25.0, 10.0))[2]):
+        total += _check_fma_report(capi, port, ctx, n, lower4, extent4, tidx, mats, np.ascontiguousarray(vp, np.float32))
+    assert total > 0, "no boundary object flipped under FMA on 16 M decisions: the report is not exercised"
+    ctx.close()
+
+
+def _check_fma_report(capi, port, ctx, n, lower4, extent4, tidx, mats, vp):
     rep = ctx.fma_report(vp)
     want = port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), vp, threads=4)
     exact = ctx.result_create()
@@ -359,7 +366,8 @@ def test_fma_mode_reports_disagreements(capi, port):
                 nearest = min(nearest, abs(clip[a] + clip[3]) / scale, abs(clip[3] - clip[a]) / scale)
         assert nearest < 1e-5, "object %d flips under FMA but is not near a clip plane (%.3g)" % (i, nearest)
     print("fma fast mode: %d of %d objects disagree with the exact path, first indices %s" % (rep["disagreements"], n, rep["first_indices"]))
-    exact.close(), ctx.close()
+    exact.close()
+    return rep["disagreements"]
 
 
 def test_error_behaviour(capi):
@@ -885,6 +893,100 @@ def test_run_with_tree_and_peer_bitsets(capi, port, fuse):
     full.download(got)
     assert np.array_equal(got[32:32 + words], want) and not got[:32].any()
     r.close(), ctx.close(), t.close(), full.close()
+
+
+def test_batched_object_edits_and_word_updates(capi, port):
+    """dpcuCullSetObjectCount / dpcuCullUpdateObjects / dpcuCullResultUpdateWords: a frame of adds, swap-removes and live
+    edits as one batch equals the same scene uploaded whole; the running transform-index maximum is recomputed before
+    it may reject a cull."""
+    n = 50000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n + 3000)
+    lower4, extent4, tidx = lower4.copy(), extent4.copy(), tidx.copy()
+    tidx[:n] %= np.uint32(n)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4[:n], extent4[:n], tidx[:n])
+    ctx.set_matrices(mats[:n + 3000].reshape(-1))
+    r = ctx.result_create()
+    vp = scenes.camera_c2()
+    ctx.run([r], vp)
+    state = r.bits().copy()
+    rng = np.random.RandomState(5)
+    # host model of the group: 700 swap-removes, 1200 appends, 4000 live edits
+    lo, ex, ti = lower4[:n].copy(), extent4[:n].copy(), tidx[:n].copy()
+    bits = np.unpackbits(state.view(np.uint8), bitorder="little")[:n].copy()
+    touched = set()
+    for gi in rng.randint(0, n - 800, size=700):
+        last = len(ti) - 1
+        lo[gi], ex[gi], ti[gi] = lo[last], ex[last], ti[last]
+        lo, ex, ti = lo[:last], ex[:last], ti[:last]
+        bits[gi] = bits[last]                                   # ResultBitSet::onNotify: the bit follows the object
+        touched.add(int(gi))
+    lo = np.concatenate([lo, lower4[n:n + 1200]]); ex = np.concatenate([ex, extent4[n:n + 1200]]); ti = np.concatenate([ti, tidx[n:n + 1200]])
+    touched.update(range(len(ti) - 1200, len(ti)))
+    edit = rng.choice(len(ti), size=4000, replace=False)
+    ex[edit, :3] *= 3.0
+    ti[edit] = rng.randint(0, n + 3000, size=4000).astype(np.uint32)
+    touched.update(int(x) for x in edit)
+    idx = np.array(sorted(touched), np.uint32)
+    # the stored result's words after the moves, written back as one batch (only words that changed)
+    moved = np.packbits(np.concatenate([bits, np.zeros((-len(bits)) % 32, np.uint8)]), bitorder="little").view(np.uint32)
+    diff = np.flatnonzero(moved != state)
+    r.update_words(diff.astype(np.uint32), moved[diff])
+    assert np.array_equal(r.bits(), moved)
+    ctx.set_object_count(len(ti))
+    ctx.update_objects(idx, lo[idx], ex[idx], ti[idx])
+    ctx.run([r], vp)
+    want = port.cull_bits(lo, ex, ti, mats.reshape(-1), vp)
+    assert np.array_equal(r.bits(), want)
+    prev = port.result_resize(moved.copy(), n, len(ti))
+    assert np.array_equal(r.changed(), port.update_changed(want, prev, len(ti)))
+    # stale maximum: point one object at the last matrix, then away again and shrink the matrix array
+    ctx.update_objects(np.array([7], np.uint32), lo[7:8], ex[7:8], np.array([n + 2999], np.uint32))
+    ctx.update_objects(np.array([7], np.uint32), lo[7:8], ex[7:8], ti[7:8])
+    keep = int(ti.max()) + 1
+    ctx.set_matrices(mats[:keep].reshape(-1))
+    ctx.run([r], vp)                                            # would be rejected on the running maximum alone
+    assert np.array_equal(r.bits(), want)
+    ctx.update_objects(np.array([7], np.uint32), lo[7:8], ex[7:8], np.array([keep], np.uint32))
+    with pytest.raises(capi.DpcuError):
+        ctx.run([r], vp)
+    r.close(), ctx.close()
+
+
+def test_tree_refresh_host_world_for_dirty_nodes_only(capi, port):
+    """dpcuTreeGetWorldDirty: the host copy of the world matrices is refreshed for exactly the nodes a compute changed."""
+    entries, offsets, n_nodes = scenes.hierarchy_topology((8, 64, 512, 8192))
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=0)
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    t.set_locals(0, local)
+    t.compute()
+    host = np.zeros_like(local)
+    host[0] = local[0]
+    assert t.refresh_host_world(host) == n_nodes - 1
+    assert np.array_equal(host.view(np.uint32), t.world().view(np.uint32))
+    # two dirty nodes at the ends of the leaf level (+ nothing else): exactly two matrices travel
+    first_leaf = n_nodes - 8192
+    for node in (first_leaf, n_nodes - 1):
+        local[node, 3, :3] += 5.0
+    t.update_locals(np.array([first_leaf, n_nodes - 1], np.uint32), local[[first_leaf, n_nodes - 1]])
+    t.compute()
+    sentinel = host.copy()
+    assert t.refresh_host_world(host) == 2
+    assert np.array_equal(host.view(np.uint32), t.world().view(np.uint32))
+    changed = np.flatnonzero((host != sentinel).any(axis=(1, 2)))
+    assert list(changed) == [first_leaf, n_nodes - 1]
+    # a dirty inner node drags its subtree along
+    local[1, 3, 0] += 1.0
+    t.update_locals(np.array([1], np.uint32), local[[1]])
+    t.compute()
+    assert t.refresh_host_world(host) == 1 + 8 + 64 + 1024
+    assert np.array_equal(host.view(np.uint32), t.world().view(np.uint32))
+    t.compute()
+    assert t.refresh_host_world(host) == 0
+    t.close()
 
 
 # ------------------------------------------------------------------ visible-instance list built on the device

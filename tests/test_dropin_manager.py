@@ -171,6 +171,52 @@ def test_live_object_edit_reaches_the_device(dropin, port):
 
 
 @pytest.mark.gpu
+def test_ten_thousand_live_edits_per_frame(dropin):
+    """a frame of an xbar-scale scene edits thousands of live objects.  262 144 objects; every frame
+    10 000 objectSetBoundingBox / objectSetTransformIndex calls on live objects, 2 000 removals (swap-remove) and 2 000
+    additions, then a cull - through the reference cpu Manager and the cuda Manager, identical bitsets and changed lists
+    frame by frame.  The cuda backend ships each frame's edits as ONE batch (dpcuCullSetObjectCount +
+    dpcuCullUpdateObjects) and the bit moves of the removals as one batch of words (dpcuCullResultUpdateWords)."""
+    import time
+    n, extra = 1 << 18, 16000
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n + extra, seed=scenes.SEED_C2 + 3)
+    a, b = RefEngine(dropin, 0), RefEngine(dropin, 1)
+    for e in (a, b):
+        e.add(lower4[:n], upper4[:n], tidx[:n])
+        e.set_matrices(mats.reshape(-1))
+    frames = cases.frames(5)
+    for e in (a, b):
+        e.cull(frames[0])
+    rng = np.random.RandomState(77)
+    have, spare = n, n
+    spent = {0: 0.0, 1: 0.0}
+    for f in range(1, 5):
+        edit = rng.choice(have, size=10000, replace=False).astype(np.uint32)
+        new_lo = lower4[edit, :3] - rng.uniform(0.0, 30.0, size=(10000, 3)).astype(np.float32)
+        new_hi = upper4[edit, :3] + rng.uniform(0.0, 30.0, size=(10000, 3)).astype(np.float32)
+        new_ti = rng.randint(0, n + extra, size=10000).astype(np.uint32)
+        gone = rng.randint(0, have - 2000, size=2000).astype(np.uint32)      # indices stay valid while the group shrinks
+        for k, e in enumerate((a, b)):
+            t0 = time.perf_counter()
+            e.s.set_objects_many(edit, new_lo, new_hi, new_ti)
+            # (the removals / additions that follow dirty the cpu backend's OBB cache; live edits alone would not -
+            # the reference quirk of SURVEY.md section 7, hard part 5)
+            e.s.remove_objects_many(gone)
+            e.add(lower4[spare:spare + 2000], upper4[spare:spare + 2000], tidx[spare:spare + 2000])
+            bits, changed = e.cull(frames[f])
+            spent[k] += time.perf_counter() - t0
+            if k == 0:
+                want = (bits, changed)
+            else:
+                assert np.array_equal(bits, want[0]), "frame %d: bits" % f
+                assert np.array_equal(changed, want[1]), "frame %d: changed list" % f
+        spare += 2000
+    print("10 000 edits + 2 000 removals + 2 000 additions + cull per frame over %d objects: reference cpu Manager %.2f ms, "
+          "cuda Manager %.2f ms per frame (host wall clock incl. the driver's loops)" % (n, 250.0 * spent[0], 250.0 * spent[1]))
+    a.close(), b.close()
+
+
+@pytest.mark.gpu
 def test_multi_view_and_device_matrices_extensions(dropin, port):
     from pipeline_b200 import capi
     n = 20000
@@ -337,3 +383,33 @@ def test_cpp_frame_loop_reference_stack_vs_cuda_stack(dropin):
     r = subprocess.run([FRAME_LOOP], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ok") and r.stdout.count("identical") == 6, r.stdout
+
+
+# ------------------------------------------------------------------ through the PATCHED dp::sg::xbar::culling::CullingImpl
+XBAR_LOOP = os.path.join(ROOT, "tests", "cpp", "_build", "xbar_loop")
+
+
+def test_patched_culling_impl_fails_loudly_without_gpu(dropin):
+    """Mode::CUDA in the patched CullingImpl has no silent CPU path: without a device Culling::create throws."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not os.path.exists(XBAR_LOOP):
+        pytest.skip("tests/cpp/_build/xbar_loop not present")
+    r = subprocess.run([XBAR_LOOP], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_patched_culling_impl_cpu_mode_vs_cuda_mode(dropin):
+    """SURVEY.md 8 a15 / f1 as code: the reference's own CullingImpl.cpp with patches/0001-culling-cuda-backend.patch
+    applied (case Mode::CUDA, device-resident matrix feed, TransformObserver attached), compiled against stand-in
+    SceneTree headers and driven through Culling::create / cull / resultGetChangedIndices / resultIsVisible /
+    getBoundingBox with SceneTree ADDED / REMOVED / CHANGED events: Mode::CPU and Mode::CUDA agree on eight frames."""
+    import subprocess
+    if not os.path.exists(XBAR_LOOP):
+        pytest.skip("tests/cpp/_build/xbar_loop not present (built only where /root/reference exists)")
+    r = subprocess.run([XBAR_LOOP], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ok") and r.stdout.count("identical") == 8, r.stdout
