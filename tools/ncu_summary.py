@@ -31,6 +31,12 @@ KEYS = {
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "lts__t_bytes.sum": "l2_bytes",
+    "smsp__inst_executed.sum": "warp_instructions",
+    "smsp__inst_executed_op_local_ld.sum": "local_loads",
+    "smsp__inst_executed_op_local_st.sum": "local_stores",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio": "stall_math_pipe",
 }
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
          "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3,
@@ -53,7 +59,7 @@ def main():
     caps = []
     for vals in rows[2:]:
         d = {"workload": a.workload, "objects": a.objects, "views": a.views, "note": a.note,
-             "source": os.path.basename(a.rep)}
+             "source": os.path.basename(a.rep), "report": os.path.basename(a.rep).replace(".ncu-rep", "")}
         for i, h in enumerate(hdr):
             if h == "Kernel Name":
                 d["kernel"] = vals[i]
