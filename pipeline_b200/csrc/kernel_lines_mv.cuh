@@ -23,11 +23,17 @@
 namespace dpcu
 {
 #ifndef DPCU_MV_MIN_CTAS
-#define DPCU_MV_MIN_CTAS 4
+#define DPCU_MV_MIN_CTAS ( DPCU_MV_RING ? 3 : 4 )
 #endif
 #ifndef DPCU_MV_PIPE
 #define DPCU_MV_PIPE 1              // 0: loads as they come, 1: transform index a step ahead, 2: 1 + L2 prefetch of the next
 #endif                              // step's matrix  (all six loads a step ahead - a register double buffer - spilled: 1.9 ms)
+#ifndef DPCU_MV_RING
+#define DPCU_MV_RING 0              // 1: the next step's six 16-byte loads per lane go to shared memory with cp.async (LDGSTS) while
+#endif                              // this step is classified - bytes in flight without registers, 3 CTAs per SM with 70 KB of shared
+                                    // memory each.  Measured: long_scoreboard 6.0 -> 2.6 warps per issue, but the 6 LDGSTS + 6 LDS.128
+                                    // per lane and step saturate the MIO queue (short_scoreboard 0.9 -> 3.2, mio_throttle 1.0) and the
+                                    // L1 shrinks to 19 KB: 1.57 ms instead of 1.245 ms at 64 Mi x 6 views.  Kept as an experiment.
 #ifndef DPCU_MV_RECOMPUTE_W
 #define DPCU_MV_RECOMPUTE_W 0       // the OBB's w components are not kept in registers across the classification
 #endif
@@ -47,11 +53,31 @@ namespace dpcu
   template <int NV>
   struct MvWarp
   {
+#if DPCU_MV_RING
+    float4   stage[6][32];                 // the NEXT step's inputs, landing while this step is classified: lowerIdx, extent, 4 matrix rows
+#endif
     float4   obb[4][kMvObjCap];            // pt, ax, ay, az of the queued objects
     uint32_t acc[NV][32];                  // ballot word of step w for view v
     uint16_t tag[kMvFlushAt + 32 * NV];    // undecided pairs: object slot << 3 | view
     uint16_t pos[kMvObjCap];               // step << 5 | lane of the queued object
   };
+
+  template <int NV> __host__ __device__ constexpr size_t mvViewTableBytes() { return ( size_t( NV ) * 8 * sizeof( f32x2 ) + 15 ) & ~size_t( 15 ); }
+  template <int NV> __host__ __device__ constexpr size_t mvSharedBytes()      // dynamic shared memory of cullLinesMvKernel
+  {
+    return DPCU_MV_RING ? mvViewTableBytes<NV>() + sizeof( MvWarp<NV> ) * ( kCullThreads / 32 ) : 0;
+  }
+
+  // 16 bytes global -> shared without a register in between (LDGSTS); .ca keeps the line in L1 like the __ldg it replaces
+  // (two matrix rows share a 32-byte sector)
+  __device__ __forceinline__ void copyAsync16( void *smem, void const *gmem )
+  {
+    asm volatile( "cp.async.ca.shared.global [%0], [%1], 16;" :: "r"( uint32_t( __cvta_generic_to_shared( smem ) ) ), "l"( gmem ) : "memory" );
+  }
+  __device__ __forceinline__ void copyAsyncWaitAll()
+  {
+    asm volatile( "cp.async.wait_all;" ::: "memory" );
+  }
 
   __device__ __forceinline__ void bulkPrefetchL2( void const *p, uint32_t bytes )
   {
@@ -80,6 +106,21 @@ namespace dpcu
     __syncwarp();
   }
 
+#if DPCU_MV_RING
+  // object `i` (already clamped) with transform index `tidx`: its six 16-byte pieces into the lane's stage slots
+  template <int NV>
+  __device__ __forceinline__ void mvStageStep( MvWarp<NV> &sh, CullArgs<NV> const &a, uint32_t i, uint32_t tidx, uint32_t lane )
+  {
+    float4 const *m = a.mats + 4ull * tidx;
+    copyAsync16( &sh.stage[0][lane], a.lowerIdx + i );
+    copyAsync16( &sh.stage[1][lane], a.extent + i );
+    copyAsync16( &sh.stage[2][lane], m + 0 );
+    copyAsync16( &sh.stage[3][lane], m + 1 );
+    copyAsync16( &sh.stage[4][lane], m + 2 );
+    copyAsync16( &sh.stage[5][lane], m + 3 );
+  }
+#endif
+
   template <int NV, bool kFuseList>
   __global__ void __launch_bounds__( kCullThreads, DPCU_MV_MIN_CTAS )
   cullLinesMvKernel( const __grid_constant__ CullArgs<NV> a )
@@ -93,9 +134,16 @@ namespace dpcu
     const uint32_t nWarps = gridDim.x * ( kCullThreads / 32 );
     uint32_t line = blockIdx.x * ( kCullThreads / 32 ) + ( threadIdx.x >> 5 );
     uint32_t pending = kNoLine;
+#if DPCU_MV_RING
+    // dynamic shared memory (more than the 48 KB a static allocation may have): the view table, then one MvWarp per warp
+    extern __shared__ __align__( 16 ) unsigned char sMvRaw[];
+    f32x2 *sP = reinterpret_cast<f32x2 *>( sMvRaw );
+    MvWarp<NV> &sh = reinterpret_cast<MvWarp<NV> *>( sMvRaw + mvViewTableBytes<NV>() )[threadIdx.x >> 5];
+#else
     __shared__ f32x2 sP[NV * 8];
     __shared__ MvWarp<NV> sWarp[kCullThreads / 32];
     MvWarp<NV> &sh = sWarp[threadIdx.x >> 5];
+#endif
     fillViewTable<NV>( sP, a );
     for ( ;; )
     {
@@ -135,6 +183,10 @@ namespace dpcu
       {
         const uint32_t i0 = min( ( word0 << 5 ) + lane, a.n - 1u );
         idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i0 ) + 3 );
+#if DPCU_MV_RING
+        mvStageStep( sh, a, i0, idxNext, lane );               // step 0 of the line (two dependent round trips, once per line)
+        if ( steps > 1 ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i0 + 32u, a.n - 1u ) ) + 3 );
+#endif
       }
 #endif
 #pragma unroll 1
@@ -145,6 +197,14 @@ namespace dpcu
         const uint32_t liveMask = __ballot_sync( 0xffffffffu, live );
         // lanes past the end re-read the last object (no branch, no zero fill); liveMask drops their results
         const uint32_t ic = min( i, a.n - 1u );
+#if DPCU_MV_RING
+        // this step's inputs were copied into the lane's own stage slots during the previous step (or just now, for
+        // the first step of the line): wait for the lane's copies, read them, and send the NEXT step's on their way
+        copyAsyncWaitAll();
+        const float4 lo = sh.stage[0][lane], ex = sh.stage[1][lane];
+        const float4 m0 = sh.stage[2][lane], m1 = sh.stage[3][lane], m2 = sh.stage[4][lane], m3 = sh.stage[5][lane];
+        const uint32_t tidx = __float_as_uint( lo.w );
+#else
 #if DPCU_MV_PIPE >= 1
         const uint32_t tidx = idxNext;
 #endif
@@ -161,7 +221,16 @@ namespace dpcu
 #if DPCU_MV_PIPE >= 1
         if ( w + 1 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 32u, a.n - 1u ) ) + 3 );
 #endif
+#endif
         Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+#if DPCU_MV_RING
+        if ( w + 1 < steps )
+        {
+          // (the stage slots were read into registers and consumed by makeObb above; asm volatile keeps the order)
+          mvStageStep( sh, a, min( i + 32u, a.n - 1u ), idxNext, lane );
+          if ( w + 2 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 64u, a.n - 1u ) ) + 3 );
+        }
+#endif
 #if DPCU_MV_PREFETCH
         {
           // step w + DIST of this line: object runs always; matrices when this step's indices are consecutive
