@@ -426,11 +426,6 @@ namespace dpcu
     if ( useStaged && !ctx->optChanged ) DPCU_CUDA( cudaMemsetAsync( results[0]->donePtr(), 0, 16, stream ) );
     const size_t stagedSmem = sizeof( WarpRing ) * ( kCullThreads / 32 );
     if ( useStaged ) DPCU_CUDA( cudaFuncSetAttribute( cullStagedKernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( stagedSmem ) ) );
-    if ( useLinesMv && mvSharedBytes<NV>() )
-    {
-      DPCU_CUDA( cudaFuncSetAttribute( cullLinesMvKernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( mvSharedBytes<NV>() ) ) );
-      DPCU_CUDA( cudaFuncSetAttribute( cullLinesMvKernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( mvSharedBytes<NV>() ) ) );
-    }
     args.vpFinite = 1;
     args.onePair  = 0x3f8000003f800000ull;
     for ( int k = 0; k < 16 * NV; ++k )
@@ -443,8 +438,8 @@ namespace dpcu
     if ( perSm <= 0 )
     {
       if ( useFused ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullFusedLeafKernel<NV>, kCullThreads, 0 );
-      else if ( useLinesMv && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, true>, kCullThreads, mvSharedBytes<NV>() );
-      else if ( useLinesMv ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, false>, kCullThreads, mvSharedBytes<NV>() );
+      else if ( useLinesMv && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, true>, kCullThreads, 0 );
+      else if ( useLinesMv ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesMvKernel<NV, false>, kCullThreads, 0 );
       else if ( useLines && fuseList ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, true>, kCullThreads, 0 );
       else if ( useLines ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullLinesKernel<NV, false>, kCullThreads, 0 );
       else if ( useGrid ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullGridKernel<NV>, kCullThreads, 0 );
@@ -488,8 +483,8 @@ namespace dpcu
       const uint32_t nLines = uint32_t( divUp( divUp( ctx->n, 32 ), args.lineWords ) );
       const uint32_t ctasForLines = uint32_t( divUp( nLines, kCullThreads / 32 ) );
       if ( uint32_t( grid ) > ctasForLines ) grid = int( ctasForLines );
-      if ( useLinesMv && fuseList ) cullLinesMvKernel<NV, true><<<grid, kCullThreads, mvSharedBytes<NV>(), stream>>>( args );
-      else if ( useLinesMv )        cullLinesMvKernel<NV, false><<<grid, kCullThreads, mvSharedBytes<NV>(), stream>>>( args );
+      if ( useLinesMv && fuseList ) cullLinesMvKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
+      else if ( useLinesMv )        cullLinesMvKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
       else if ( fuseList )          cullLinesKernel<NV, true><<<grid, kCullThreads, 0, stream>>>( args );
       else                          cullLinesKernel<NV, false><<<grid, kCullThreads, 0, stream>>>( args );
       DPCU_CUDA( cudaGetLastError() );
