@@ -256,6 +256,74 @@ def test_view_counts_both_kernels(capi, port, kernel, nv):
     _check_views(capi, port, kernel, lower4, extent4, tidx, mats, _views_for(nv), frames=2)
 
 
+@pytest.mark.parametrize("kernel", ["lines_pairs", "lines_pairs_compact", "grid", "lines", "auto"])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1023, 1024, 1025, 2047, 4097, 33000])
+def test_ragged_sizes_multi_view(capi, port, kernel, n):
+    """line / tile / word boundaries of the line-granular and grid forms: 1 object ... a few lines, 3 and 6 views,
+    two frames (the second one exercises the changed list against non-trivial previous bits)"""
+    lower4, extent4, upper4, mats, tidx = cases.random_case(max(n, 64), seed=scenes.SEED_C4 + n)
+    lower4, extent4 = lower4[:n], extent4[:n]
+    tidx = (tidx[:n] % np.uint32(n)).astype(np.uint32)
+    for nv in (3, 6):
+        _check_views(capi, port, kernel, lower4, extent4, tidx, mats[:max(n, 1)], _views_for(nv), frames=2)
+
+
+def test_results_of_one_run_must_share_their_peer_layout(capi):
+    """one kernel stores every view's lines into the peers, so results that disagree on peer count / word
+    offset are rejected instead of being written at the wrong offset"""
+    lower4, extent4, upper4, mats, tidx = cases.random_case(5000)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(mats.reshape(-1))
+    r0, r1 = ctx.result_create(), ctx.result_create()
+    full = capi.Buffer(64 * 1024)
+    full.fill(0)
+    r0.set_peer_bits([full.ptr], 0)
+    with pytest.raises(capi.DpcuError):
+        ctx.run([r0, r1], _views_for(2))                  # r1 has no peers
+    r1.set_peer_bits([full.ptr], 1024)
+    with pytest.raises(capi.DpcuError):
+        ctx.run([r0, r1], _views_for(2))                  # different word offsets
+    r1.set_peer_bits([full.ptr], 0)
+    ctx.run([r0, r1], _views_for(2))
+    r0.close(), r1.close(), ctx.close(), full.close()
+
+
+def test_run_with_tree_that_fails_early_leaves_the_tree_dirty(capi, port):
+    """a dpcuCullRunWithTree that is rejected (here: a host mirror that is too small) must not consume the
+    tree's dirty bits - the next, valid call still propagates everything, the fused leaf level included."""
+    levels = (4, 32, 2048)
+    entries, offsets, n_nodes = scenes.hierarchy_topology(levels)
+    n = levels[-1]
+    local = np.zeros((n_nodes, 4, 4), np.float32)
+    local[0] = np.eye(4, dtype=np.float32)
+    local[1:] = scenes.hierarchy_locals(scenes.SEED_C3, 1, n_nodes - 1, frame=2)
+    lower4, extent4, upper4, _, _ = cases.random_case(n)
+    tidx = np.arange(n_nodes - n, n_nodes, dtype=np.uint32)
+    t = capi.Tree(0)
+    t.set_topology(entries, offsets, n_nodes)
+    t.set_locals(0, local)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    r = ctx.result_create()
+    small = [capi.HostBuffer(8), capi.HostBuffer(n * 4), capi.HostBuffer(4)]
+    r.set_host_mirror(small[0].array(np.uint32), small[1].array(np.uint32), small[2].array(np.uint32))
+    vp = scenes.mat_mul(scenes.make_look_at((0, 0, 150), (0, 0, 0), (0, 1, 0)), scenes.make_perspective(40.0, 1.3, 1.0, 500.0))
+    with pytest.raises(capi.DpcuError):
+        ctx.run_with_tree(t, [r], vp)                     # mirror holds 2 words, 64 needed: rejected before any launch
+    r.set_host_mirror(None, None, None)
+    ctx.run_with_tree(t, [r], vp)
+    world = np.zeros_like(local)
+    world[0] = local[0]
+    nw = (n_nodes + 31) // 32
+    port.tree_compute(local, world, entries, offsets, np.full(nw, 0xFFFFFFFF, np.uint32), np.zeros(nw, np.uint32))
+    assert np.array_equal(t.world().view(np.uint32), world.view(np.uint32))
+    assert np.array_equal(r.bits(), port.cull_bits(lower4, extent4, tidx, world.reshape(-1), vp))
+    r.close(), ctx.close(), t.close()
+    for b in small:
+        b.close()
+
+
 @pytest.mark.parametrize("kernel", sorted(KERNELS))
 def test_non_affine_and_special_values_multi_view(capi, port, kernel):
     """Projective / NaN / Inf world matrices force the views kernel's general path, the affine
