@@ -242,7 +242,7 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 /* Tuning / reporting knobs (never change results unless stated). */
 #define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
 #define DPCU_KERNEL_AUTO    0           /* the measured winner: line-granular (list built in-kernel) for groups */
-                                        /* of >= 29 M (1 view) / 4.8 M (more views) objects and whenever peer   */
+                                        /* of >= 29 M (1 view) / 3.1 M (2 views) / 2.1 M (more) objects and with peer */
                                         /* bitsets are set; else direct                                         */
                                         /* (1 view) / view-sequential packed (>= 2 views)                       */
 #define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */

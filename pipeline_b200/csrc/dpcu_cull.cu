@@ -378,7 +378,9 @@ namespace dpcu
     // (The same kernel with 8 or 16 bitset words per warp - DPCU_CULL_OPT_LINE_WORDS - fills the machine on
     // mid-size groups but does not beat direct + compaction there either: 1 / 2 / 4 Mi objects 57 / 81 / 114 us vs
     // 48 / 70 / 108 us per step.)
-    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 4u * 48u : 32u );
+    // (round 2, pair-filter form against views + compaction, step time with the L2 flushed: 6 views 1.5 Mi objects 79 vs 77 us,
+    // 2 Mi 84 vs 95 us, 3 Mi 100 vs 128 us, 4 Mi 116 vs 157 us; 2 views 2 Mi 63 vs 62 us, 3 Mi 77 vs 79 us, 4 Mi 94 vs 97 us)
+    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 4u * 48u : ( NV == 2 ? 21u : 14u ) );
     const bool bigEnough = divUp( divUp( ctx->n, 32 ), 32 ) >= wantedLines;
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );

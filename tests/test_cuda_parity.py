@@ -363,16 +363,20 @@ def test_views_kernel_four_million_objects_six_views(capi, port):
     ctx = capi.Cull(0)
     ctx.set_objects(lower4, extent4, tidx)
     ctx.set_matrices(mats.reshape(-1))
-    assert ctx.get_option(capi.OPT_KERNEL) == 0          # auto -> views kernel for 6 views
-    res = [ctx.result_create() for _ in range(6)]
-    ctx.run(res, vps)
+    assert ctx.get_option(capi.OPT_KERNEL) == 0
     flat = mats.reshape(-1)
-    for v in range(6):
-        want = port.cull_bits(lower4, extent4, tidx, flat, vps[v], threads=8)
-        got = res[v].bits()
-        assert np.array_equal(got, want), "view %d: %d of %d objects differ" % (v, popcount(got ^ want), n)
-    for r in res:
-        r.close()
+    want = [port.cull_bits(lower4, extent4, tidx, flat, vps[v], threads=8) for v in range(6)]
+    # AUTO takes the pair-filter line-granular kernel at this size; the view-sequential kernel is asked for explicitly
+    for kernel, ran in ((capi.KERNEL_AUTO, capi.KERNEL_LINES_PAIRS), (capi.KERNEL_VIEWS, capi.KERNEL_VIEWS)):
+        ctx.set_option(capi.OPT_KERNEL, kernel)
+        res = [ctx.result_create() for _ in range(6)]
+        ctx.run(res, vps)
+        assert ctx.get_option(capi.OPT_LAST_KERNEL) == ran
+        for v in range(6):
+            got = res[v].bits()
+            assert np.array_equal(got, want[v]), "kernel %d view %d: %d of %d objects differ" % (kernel, v, popcount(got ^ want[v]), n)
+        for r in res:
+            r.close()
     ctx.close()
 
 
