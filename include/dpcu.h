@@ -242,7 +242,7 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 /* Tuning / reporting knobs (never change results unless stated). */
 #define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
 #define DPCU_KERNEL_AUTO    0           /* the measured winner: line-granular (list built in-kernel) for groups */
-                                        /* of >= 29 M (1 view) / 3.1 M (2 views) / 2.1 M (more) objects and with peer */
+                                        /* of >= 43.6 M (1 view) / 7.0 M (2) / 3.6 M (3) / 3.0 M (4) / 2.6 M (5+ views) objects and when peer */
                                         /* bitsets are set; else direct                                         */
                                         /* (1 view) / view-sequential packed (>= 2 views)                       */
 #define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */
@@ -274,6 +274,12 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* used by the tests to measure the slack of the proof                           */
 #define DPCU_CULL_OPT_LINE_WORDS   10   /* line-granular kernel: bitset words per warp; 0 (default) = 32 (a 128-byte */
                                         /* line); 8 / 16 = shorter lines (more warps on small groups; experiment)    */
+#define DPCU_CULL_OPT_LIST_OFFSETS 11   /* one thread per object forms (direct, views): who turns flipped bits into list offsets  */
+                                        /* 0 (default) = AUTO; 1 = the cull kernel counts flips per 8192-object segment and its   */
+                                        /* last CTA scans the counters; 2 = no counters at all, every compaction CTA popcounts    */
+                                        /* the flipped-bit words before its segment (groups <= 2 Mi objects); 3 = counters, every */
+                                        /* compaction CTA sums the counters before its segment (groups <= 32 Mi objects; no fence, */
+                                        /* ticket or serial scan at the end of the cull kernel).  Larger groups fall back to 1     */
 #define DPCU_CULL_OPT_LAST_KERNEL   8   /* read-only: DPCU_KERNEL_* form the last cull ran                          */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);

@@ -126,11 +126,12 @@ struct dpcuCull
   float const *boundMats = nullptr;      // borrowed device matrices (dpcuCullBindMatrices)
   dpcuTree    *boundTree = nullptr;      // ... of this tree (dpcuCullBindTree / dpcuCullRunWithTree): culls and its computes are ordered by events
   size_t       n = 0, nMats = 0;
+  int          occupancy[11][DPCU_MAX_VIEWS] = {};   // resident CTAs per SM by kernel form and view count (0 = not asked yet)
   uint32_t     maxTransformIndex = 0;
   bool         maxIndexKnown = true;
   bool         maxIndexStale = false;    // objects were overwritten / removed since the running maximum was started
   dpcu::StreamFence stagingFree;         // the last upload out of `staging` (the next user waits for it, not the caller)
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1, optLineWords = 0;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1, optLineWords = 0, optListOffsets = 0;
   int          lastKernel = 0;           // DPCU_KERNEL_* of the last cull launched (DPCU_CULL_OPT_LAST_KERNEL)
   uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
   dpcuTree    *leafTree = nullptr;       // cached answer of the leaf-binding check of dpcuCullRunWithTree
@@ -316,9 +317,11 @@ namespace dpcu
     ( half ? f.qw.y : f.qw.x ) = usable ? roundUp( marginScale * qw / 131072.0 ) : 0.0f;
   }
 
+  constexpr int kAutoListOffsets = 3;
+
   template <int NV>
   static int launchCull( dpcuCull *ctx, dpcuCullResult *const *results, float const *vps, cudaStream_t stream, LeafArgs const *leaf,
-                         bool *mirrorsWritten, bool *listBuilt )
+                         bool *mirrorsWritten, bool *listBuilt, int *listOffsets )
   {
     CullArgs<NV> args;
     memset( &args, 0, sizeof args );
@@ -380,7 +383,12 @@ namespace dpcu
     // 48 / 70 / 108 us per step.)
     // (round 2, pair-filter form against views + compaction, step time with the L2 flushed: 6 views 1.5 Mi objects 79 vs 77 us,
     // 2 Mi 84 vs 95 us, 3 Mi 100 vs 128 us, 4 Mi 116 vs 157 us; 2 views 2 Mi 63 vs 62 us, 3 Mi 77 vs 79 us, 4 Mi 94 vs 97 us)
-    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 4u * 48u : ( NV == 2 ? 21u : 14u ) );
+    // (round 2, after the compaction kernel took over the segment counters' prefix - DPCU_CULL_OPT_LIST_OFFSETS - the one thread
+    // per object forms gained 2-14 us per step and the crossovers moved up; step time, L2 flushed, lines vs views / direct +
+    // compaction: 6 views 2 Mi 79 vs 75 us, 3 Mi 97 vs 104 us; 4 views 3 Mi 83 vs 83 us, 4 Mi 97 vs 108 us; 3 views 3 Mi 79 vs
+    // 75 us, 4 Mi 93 vs 95 us; 2 views 6 Mi 130 vs 120 us, 8 Mi 146 vs 155 us; 1 view 24 Mi 398 vs 388 us, 32 Mi 519 vs 515 us,
+    // 40 Mi 641 vs 642 us, 64 Mi 1.011 vs 1.013 ms)
+    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 6u * 48u : NV == 2 ? 46u : NV == 3 ? 24u : NV == 4 ? 20u : 17u );
     const bool bigEnough = divUp( divUp( ctx->n, 32 ), 32 ) >= wantedLines;
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
@@ -424,6 +432,17 @@ namespace dpcu
     const bool useChains = ctx->optKernel == DPCU_KERNEL_VIEWS_CHAINS;
     const bool useViews  = !useFused && !useLines && !useGrid && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || useChains || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
+    // one thread per object forms on small groups: all list bookkeeping moves into the compaction kernel (DPCU_CULL_OPT_SCAN_SEGS)
+    // (DPCU_CULL_OPT_LIST_OFFSETS; *listOffsets = 1: last-CTA scan, 2: compaction popcounts words, 3: compaction sums counters)
+    *listOffsets = 1;
+    if ( !useFused && !useLines && !useGrid && !useStaged && ctx->optChanged )
+    {
+      int want = ctx->optListOffsets ? ctx->optListOffsets : kAutoListOffsets;
+      if ( want == 2 && args.nSegs > 256u ) want = 3;
+      if ( want == 3 && args.nSegs > 4096u ) want = 1;
+      *listOffsets = want;
+    }
+    args.countSegs = *listOffsets == 2 ? 0 : *listOffsets == 3 ? 2 : 1;
     // the last CTA's scan re-arms ticket and chunk counter; without a changed list nobody does
     if ( useStaged && !ctx->optChanged ) DPCU_CUDA( cudaMemsetAsync( results[0]->donePtr(), 0, 16, stream ) );
     const size_t stagedSmem = sizeof( WarpRing ) * ( kCullThreads / 32 );
@@ -437,6 +456,10 @@ namespace dpcu
       if ( ( u & 0x7f800000u ) == 0x7f800000u ) args.vpFinite = 0;
     }
     int perSm = ctx->optCtasPerSm;
+    // the occupancy query costs a microsecond or two of every cull on the host: asked once per kernel form and view count
+    const int form = useFused ? 0 : ( useLinesMv && fuseList ) ? 1 : useLinesMv ? 2 : ( useLines && fuseList ) ? 3 : useLines ? 4 : useGrid ? 5 : ctx->optFma ? 6
+                   : useStaged ? 7 : ( useViews && useChains ) ? 8 : useViews ? 9 : 10;
+    if ( perSm <= 0 ) perSm = ctx->occupancy[form][NV - 1];
     if ( perSm <= 0 )
     {
       if ( useFused ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullFusedLeafKernel<NV>, kCullThreads, 0 );
@@ -451,6 +474,7 @@ namespace dpcu
       else if ( useViews ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullViewsKernel<NV, true>, kCullThreads, 0 );
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, cullDirectKernel<NV>, kCullThreads, 0 );
       if ( perSm <= 0 ) perSm = 1;
+      ctx->occupancy[form][NV - 1] = perSm;
     }
     int grid = ctx->smCount * perSm;
     if ( uint32_t( grid ) > args.nTiles ) grid = int( args.nTiles );
@@ -897,16 +921,17 @@ extern "C"
     }
     int rc = DPCU_OK;
     bool mirrorsWritten = false, listBuilt = false;
+    int listOffsets = 1;
     switch ( nViews )
     {
-      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
-      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt ); break;
+      case 1: rc = dpcu::launchCull<1>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 2: rc = dpcu::launchCull<2>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 3: rc = dpcu::launchCull<3>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 4: rc = dpcu::launchCull<4>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 5: rc = dpcu::launchCull<5>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 6: rc = dpcu::launchCull<6>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 7: rc = dpcu::launchCull<7>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
+      case 8: rc = dpcu::launchCull<8>( ctx, results, viewProjections, s, leaf, &mirrorsWritten, &listBuilt, &listOffsets ); break;
     }
     DPCU_TRY( rc );
     if ( ctx->optChanged && !listBuilt )
@@ -918,6 +943,12 @@ extern "C"
         dpcuCullResult *r = results[v];
         ca.chg[v] = static_cast<uint32_t const *>( r->chg.ptr );
         ca.prefix[v] = r->prefixPtr();
+        ca.seg[v] = r->segPtr();
+        if ( !mirrorsWritten && r->dBits )
+        {
+          ca.bits[v] = static_cast<uint32_t const *>( r->bits.ptr );
+          ca.hostBits[v] = r->dBits;
+        }
         ca.changed[v] = static_cast<uint32_t *>( r->changed.ptr );
         ca.hostChanged[v]  = r->dChanged;
         ca.hostCount[v]    = r->dCount;
@@ -925,6 +956,8 @@ extern "C"
       }
       ca.nWords = uint32_t( dpcu::divUp( n, 32 ) );
       ca.nSegs = uint32_t( nSegs );
+      ca.selfPrefix = listOffsets == 2 ? 1 : listOffsets == 3 ? 2 : 0;
+      ca.done = results[0]->donePtr();
       // programmatic dependent launch: the compaction CTAs are placed while the cull kernel drains and wait in
       // cudaGridDependencySynchronize() for its memory - the launch latency of the second kernel is off the critical
       // path (it was a quarter of the step at 1 Mi objects)
@@ -939,6 +972,7 @@ extern "C"
       cfg.numAttrs = 1;
       DPCU_CUDA( cudaLaunchKernelEx( &cfg, dpcu::compactChangedKernel, ca ) );
       ++ctx->launches;
+      mirrorsWritten = true;
     }
     if ( leaf && results[0]->nPeers > 0 )
     {
@@ -1368,6 +1402,7 @@ extern "C"
       case DPCU_CULL_OPT_FILTER:       DPCU_REQUIRE( value >= 0 && value <= 3, "filter must be 0..3" ); ctx->optFilter = value; break;
       case DPCU_CULL_OPT_LINE_WORDS:   DPCU_REQUIRE( value == 0 || value == 8 || value == 16 || value == 32, "line words must be 0 (auto), 8, 16 or 32" );
                                        ctx->optLineWords = value; break;
+      case DPCU_CULL_OPT_LIST_OFFSETS: DPCU_REQUIRE( value >= 0 && value <= 3, "list offsets must be 0..3" ); ctx->optListOffsets = value; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -1388,6 +1423,7 @@ extern "C"
       case DPCU_CULL_OPT_LAST_KERNEL:  *value = ctx->lastKernel; break;
       case DPCU_CULL_OPT_FILTER:       *value = ctx->optFilter; break;
       case DPCU_CULL_OPT_LINE_WORDS:   *value = ctx->optLineWords; break;
+      case DPCU_CULL_OPT_LIST_OFFSETS: *value = ctx->optListOffsets; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
     return DPCU_OK;

@@ -38,6 +38,8 @@ namespace dpcu
     uint32_t      nPeers;
     uint32_t      peerWordOffset;
     int           buildChanged;
+    int           countSegs; // DPCU_CULL_OPT_LIST_OFFSETS: 1 = flips are counted per segment (atomics) and the last CTA scans
+                             // the counters; 2 = counted, the compaction kernel sums them; 0 = not counted at all
     uint32_t      nSegs;
     uint32_t     *done;      // CTA completion ticket (last CTA scans the segment counters)
     uint32_t     *chunkCounter;   // staged kernel: next unclaimed chunk of kChunkTiles tiles

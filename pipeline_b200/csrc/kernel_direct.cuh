@@ -57,7 +57,7 @@ namespace dpcu
           {
             const uint32_t c = oldBits[v] ^ nw;
             o.chg[word] = c;
-            if ( c )
+            if ( c && a.countSegs )
             {
               // one counter per 8192 objects: concurrently running CTAs spread over ~40 addresses.
               // (A second, coarser level of counters was measured to serialise in L2: +0.5 ms at 64 Mi objects.)
@@ -67,6 +67,6 @@ namespace dpcu
         }
       }
     }
-    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+    if ( a.buildChanged && a.countSegs == 1 ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
 }

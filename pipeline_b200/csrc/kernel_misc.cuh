@@ -11,13 +11,19 @@ namespace dpcu
   struct CompactArgs
   {
     uint32_t const *chg[DPCU_MAX_VIEWS];
-    uint32_t const *prefix[DPCU_MAX_VIEWS];
+    uint32_t       *prefix[DPCU_MAX_VIEWS];
     uint32_t       *changed[DPCU_MAX_VIEWS];
     uint32_t       *hostChanged[DPCU_MAX_VIEWS];    // optional mirror of the list in pinned host memory ...
     uint32_t       *hostCount[DPCU_MAX_VIEWS];      // ... and of its length
     uint32_t        hostCapacity[DPCU_MAX_VIEWS];
     uint32_t        nWords;
     uint32_t        nSegs;
+    int             selfPrefix;   // prefix[] holds nothing yet: 1 = every CTA popcounts the words before its segment itself,
+                                  // 2 = every CTA sums the segment counters before its own (and the last one to do so zeroes them)
+    uint32_t       *seg[DPCU_MAX_VIEWS];
+    uint32_t const *bits[DPCU_MAX_VIEWS];           // optional: the new visibility words ...
+    uint32_t       *hostBits[DPCU_MAX_VIEWS];       // ... and their mirror in pinned host memory (stored by this kernel, segment by segment)
+    uint32_t       *done;         // mode 2: ticket of the CTAs that have read the counters
   };
 
   __global__ void __launch_bounds__( 256 ) compactChangedKernel( const __grid_constant__ CompactArgs a )
@@ -28,18 +34,108 @@ namespace dpcu
     // launched with programmatic stream serialization behind the cull kernel: wait for its results here
     // (a no-op when the launch carries no such dependency, e.g. behind segmentPopcountKernel)
     cudaGridDependencySynchronize();
-    const uint32_t base0 = a.prefix[v][s];
-    const uint32_t count = a.prefix[v][s + 1] - base0;
-    if ( s == 0 && threadIdx.x == 0 && a.hostCount[v] ) *a.hostCount[v] = a.prefix[v][a.nSegs];
-    if ( count == 0 ) return;                        // nothing changed in this segment
-
     // the segment's indices are expanded into shared memory first, so that the list (and its host
     // mirror, over PCIe) is written as one contiguous, coalesced run per segment
     __shared__ uint32_t sIdx[1u << kSegObjectsLog2];
     __shared__ uint32_t sWarp[8];
+    __shared__ uint32_t sBefore[8];
     const uint32_t w = s * kSegWords + threadIdx.x;
     uint32_t c = ( w < a.nWords ) ? a.chg[v][w] : 0u;
+    // the bitset mirror of the forms that do not store whole lines themselves (direct, views, staged, fused leaf): the
+    // segment's 1 KiB crosses PCIe from here, coalesced, instead of as a copy queued behind this kernel (15 us per step
+    // at 1 Mi objects: copy-engine start-up and completion)
+    if ( a.hostBits[v] && w < a.nWords ) a.hostBits[v][w] = __ldcg( a.bits[v] + w );
     const uint32_t pc = __popc( c );
+    uint32_t base0, count;
+    if ( a.selfPrefix == 2 )
+    {
+      // The cull kernel counted flips per segment (fire-and-forget atomics) and stopped there: no fence, no ticket, no
+      // serial scan by its last CTA.  This CTA sums the counters before its own - one L2 round trip for up to 1024
+      // segments - and the last CTA to have read them zeroes them for the next cull.
+      uint32_t *seg = a.seg[v];
+      uint32_t before = 0, mine = 0;
+      for ( uint32_t k = threadIdx.x; k <= s; k += 256 )
+      {
+        const uint32_t x = __ldcg( seg + k );
+        if ( k < s ) before += x; else mine = x;
+      }
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 )
+      {
+        before += __shfl_xor_sync( 0xffffffffu, before, d );
+        mine   += __shfl_xor_sync( 0xffffffffu, mine, d );
+      }
+      if ( lane == 0 ) { sBefore[warp] = before; sWarp[warp] = mine; }
+      __syncthreads();
+      base0 = 0; count = 0;
+#pragma unroll
+      for ( int k = 0; k < 8; ++k ) { base0 += sBefore[k]; count += sWarp[k]; }
+      __syncthreads();                               // sWarp is reused by the scan below
+      if ( threadIdx.x == 0 )
+      {
+        a.prefix[v][s] = base0;
+        if ( s == a.nSegs - 1 )
+        {
+          a.prefix[v][a.nSegs] = base0 + count;
+          if ( a.hostCount[v] ) *a.hostCount[v] = base0 + count;
+        }
+      }
+      // every thread's counter reads are complete (their values went through the barrier above)
+      __shared__ uint32_t sLast;
+      if ( threadIdx.x == 0 ) sLast = ( atomicAdd( a.done, 1u ) == gridDim.x * gridDim.y - 1 ) ? 1u : 0u;
+      __syncthreads();
+      if ( sLast )
+      {
+        for ( uint32_t vv = 0; vv < gridDim.y; ++vv )
+          for ( uint32_t k = threadIdx.x; k < a.nSegs; k += 256 ) a.seg[vv][k] = 0u;
+        if ( threadIdx.x == 0 ) *a.done = 0u;
+      }
+    }
+    else if ( a.selfPrefix )
+    {
+      // Small groups (DPCU_CULL_OPT_SCAN_SEGS): the cull kernel kept no counters.  The flips before this segment are
+      // the popcount of s KiB of flipped-bit words, read from L2 as 16-byte vectors (<= 255 KiB, a microsecond); in
+      // exchange the cull kernel loses its atomics, its fence and the last-CTA scan, which were 4 us of a 27 us kernel
+      // at 1 Mi objects.
+      uint4 const *q = reinterpret_cast<uint4 const *>( a.chg[v] );
+      const uint32_t nVec = s * ( kSegWords / 4 );
+      uint32_t before = 0;
+#pragma unroll 16
+      for ( uint32_t k = threadIdx.x; k < nVec; k += 256 )
+      {
+        const uint4 x = __ldcg( q + k );
+        before += __popc( x.x ) + __popc( x.y ) + __popc( x.z ) + __popc( x.w );
+      }
+      uint32_t mine = pc;
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 )
+      {
+        before += __shfl_xor_sync( 0xffffffffu, before, d );
+        mine   += __shfl_xor_sync( 0xffffffffu, mine, d );
+      }
+      if ( lane == 0 ) { sBefore[warp] = before; sWarp[warp] = mine; }
+      __syncthreads();
+      base0 = 0; count = 0;
+#pragma unroll
+      for ( int k = 0; k < 8; ++k ) { base0 += sBefore[k]; count += sWarp[k]; }
+      __syncthreads();                               // sWarp is reused by the scan below
+      if ( threadIdx.x == 0 )
+      {
+        a.prefix[v][s] = base0;
+        if ( s == a.nSegs - 1 )
+        {
+          a.prefix[v][a.nSegs] = base0 + count;
+          if ( a.hostCount[v] ) *a.hostCount[v] = base0 + count;
+        }
+      }
+    }
+    else
+    {
+      base0 = a.prefix[v][s];
+      count = a.prefix[v][s + 1] - base0;
+      if ( s == 0 && threadIdx.x == 0 && a.hostCount[v] ) *a.hostCount[v] = a.prefix[v][a.nSegs];
+    }
+    if ( count == 0 ) return;                        // nothing changed in this segment
     uint32_t incl = pc;
 #pragma unroll
     for ( int d = 1; d < 32; d <<= 1 )

@@ -96,13 +96,13 @@ namespace dpcu
         {
           const uint32_t c = oldBits ^ myWord;
           o.chg[word] = c;
-          if ( c ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
+          if ( c && a.countSegs ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
         }
       }
 #if DPCU_VIEWS_PREFETCH
       idxNext = idxNext2;
 #endif
     }
-    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+    if ( a.buildChanged && a.countSegs == 1 ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
 }

@@ -207,14 +207,22 @@ def test_multi_view_equals_single_views(capi, port):
 # ------------------------------------------------------------------ both exact kernel forms, 1..8 views
 # every exact form of K2: DPCU_KERNEL_* plus, for the line-granular kernel, how the changed list is built
 # (inside the kernel by single-pass look-back, the default, or by segment counters + the compaction kernel)
+# (and, for the one-thread-per-object forms, who turns the flipped bits into list offsets, DPCU_CULL_OPT_LIST_OFFSETS:
+# "_scan" = per-segment counters scanned by the cull kernel's last CTA, "_words" = no counters, the compaction kernel
+# popcounts the words before each segment; the default sums the counters in the compaction kernel)
 KERNELS = {"direct": 1, "staged": 2, "views": 3, "lines": 4, "views_chains": 5, "lines_compact": 4, "lines_w8": 4,
-           "lines_pairs": 7, "lines_pairs_compact": 7, "grid": 8}
+           "lines_pairs": 7, "lines_pairs_compact": 7, "grid": 8, "direct_scan": 1, "views_scan": 3, "direct_words": 1,
+           "views_words": 3}
 
 
 def _select_kernel(capi, ctx, kernel):
     ctx.set_option(capi.OPT_KERNEL, dict(KERNELS, auto=0)[kernel])
     if kernel.endswith("_compact"):
         ctx.set_option(capi.OPT_FUSE_LIST, 0)
+    if kernel.endswith("_scan"):
+        ctx.set_option(capi.OPT_LIST_OFFSETS, 1)
+    if kernel.endswith("_words"):
+        ctx.set_option(capi.OPT_LIST_OFFSETS, 2)
     if kernel.endswith("_w8"):
         ctx.set_option(capi.OPT_LINE_WORDS, 8)              # a warp per 256 objects (the mid-size form)
 
@@ -254,6 +262,35 @@ def test_view_counts_both_kernels(capi, port, kernel, nv):
     n = 30011                                  # ragged: partial last warp and tile
     lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=scenes.SEED_C4)
     _check_views(capi, port, kernel, lower4, extent4, tidx, mats, _views_for(nv), frames=2)
+
+
+@pytest.mark.parametrize("nv", [1, 2])
+def test_list_offset_modes_many_segments(capi, port, nv):
+    """DPCU_CULL_OPT_LIST_OFFSETS on a group of 3 Mi objects (384 segments): the last-CTA scan, the compaction kernel
+    popcounting the flipped-bit words (falls back to summing counters above 256 segments) and the compaction kernel
+    summing the segment counters produce the reference's changed list (ResultBitSet.cpp:61-108), frame after frame,
+    and leave their counters clean for the next cull whichever mode that one uses."""
+    n = 3 * (1 << 20) + 4321
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=77)
+    flat = mats.reshape(-1)
+    ctx = capi.Cull(0)
+    ctx.set_objects(lower4, extent4, tidx)
+    ctx.set_matrices(flat)
+    ctx.set_option(capi.OPT_KERNEL, capi.KERNEL_DIRECT if nv == 1 else capi.KERNEL_VIEWS)
+    res = [ctx.result_create() for _ in range(nv)]
+    state = [port.result_resize(np.zeros(0, np.uint32), 0, n) for _ in range(nv)]
+    frames = cases.frames(6)
+    for f, mode in enumerate((3, 1, 2, 3, 0, 1)):
+        ctx.set_option(capi.OPT_LIST_OFFSETS, mode)
+        vps = np.ascontiguousarray(np.stack([frames[(f + v) % 6] for v in range(nv)]), np.float32)
+        ctx.run(res, vps)
+        for v in range(nv):
+            want = port.cull_bits(lower4, extent4, tidx, flat, vps[v], threads=8)
+            assert np.array_equal(res[v].bits(), want), (mode, f, v)
+            assert np.array_equal(res[v].changed(), port.update_changed(want, state[v], n)), (mode, f, v)
+    for r in res:
+        r.close()
+    ctx.close()
 
 
 @pytest.mark.parametrize("kernel", ["lines_pairs", "lines_pairs_compact", "grid", "lines", "auto"])
@@ -830,7 +867,7 @@ class _Mirror:
 
 
 @pytest.mark.parametrize("kernel", ["auto", "direct", "views", "staged", "lines", "lines_compact", "lines_w8", "lines_pairs",
-                                    "lines_pairs_compact", "grid"])
+                                    "lines_pairs_compact", "grid", "direct_scan", "views_scan", "direct_words", "views_words"])
 @pytest.mark.parametrize("nv", [1, 3])
 def test_host_mirror_matches_port(capi, port, kernel, nv):
     """dpcuCullResultSetHostMirror: after run + synchronize the pinned buffers hold exactly what

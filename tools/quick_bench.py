@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--fma", type=int, default=0)
     ap.add_argument("--changed", type=int, default=1)
     ap.add_argument("--filter", type=int, default=1, help="multi-view filter (DPCU_CULL_OPT_FILTER)")
+    ap.add_argument("--list-offsets", type=int, default=0, help="DPCU_CULL_OPT_LIST_OFFSETS")
+    ap.add_argument("--profile", type=int, default=1, help="0: no per-launch events (they sit between the cull and the dependent compaction launch)")
     ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
     ap.add_argument("--eye", type=float, nargs=3, default=None, help="multi-view: cube-map eye position")
     ap.add_argument("--move", type=float, default=0.0, help="multi-view: the eye moves by this much in x per iteration")
@@ -38,6 +40,7 @@ def main():
     ctx.set_option(capi.OPT_FMA, a.fma)
     ctx.set_option(capi.OPT_CHANGED_LIST, a.changed)
     ctx.set_option(capi.OPT_FILTER, a.filter)
+    ctx.set_option(capi.OPT_LIST_OFFSETS, a.list_offsets)
     res = [ctx.result_create() for _ in range(a.views)]
     cams = np.concatenate([scenes.cube_map_cameras(), scenes.cube_map_cameras((50.0, 20.0, -30.0))]) if a.views > 1 else None
     s = capi.Stream()
@@ -56,7 +59,7 @@ def main():
         ctx.run(res, cam[f], s)
     s.sync()
     times = []
-    ctx.set_option(capi.OPT_PROFILE, 1)
+    ctx.set_option(capi.OPT_PROFILE, a.profile)
     ctx.kernel_time()
     flush = capi.Buffer(256 << 20) if a.flush else None
     sweep = capi.Buffer(256 << 20) if a.flush == 2 else None
