@@ -666,7 +666,8 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- BASELINE config 5 next to the headline: 256 Mi objects STRONG-scaled over the N GPUs, with the bitset
     # all-gather fused into the timed step when N > 1 (the driver's 1/2/4/8 sweep then shows the c5 strong-scaling curve)
     if args.workload == "c4-single" and not args.no_also and not args.no_c5:
-        n5 = (1 << 28) // world
+        c5_total = int(os.environ.get("DPCU_BENCH_C5_TOTAL", 1 << 28))      # developer override (e.g. 2 GPUs at 8-GPU shard size)
+        n5 = c5_total // world
         first5 = rank * n5
         lo5, ex5, mt5 = capi.Buffer(n5 * 16), capi.Buffer(n5 * 16), capi.Buffer(n5 * 64)
         capi.scene_generate(WORKLOADS["c5"][2], first5, n5, first5, lo5.ptr, ex5.ptr, mt5.ptr)
@@ -675,13 +676,15 @@ def run_ours(args, rank, world, local_rank):
         ctx5.set_objects(lo5.ptr, ex5.ptr, None, capi.MEM_DEVICE, n=n5)
         ctx5.bind_matrices(mt5.ptr, n5)
         ctx5.set_option(capi.OPT_PROFILE, 1)
+        if os.environ.get("DPCU_BENCH_LINE_WORDS"):
+            ctx5.set_option(capi.OPT_LINE_WORDS, int(os.environ["DPCU_BENCH_LINE_WORDS"]))
         r5 = ctx5.result_create()
         g5 = "none (1 GPU)"
         fb5 = None
         ok5 = None
         if world > 1:
             from pipeline_b200 import sharding
-            fb5 = capi.Buffer(sharding.total_words(1 << 28) * 4)
+            fb5 = capi.Buffer(sharding.total_words(c5_total) * 4)
             fb5.fill(0)
             handles = sharding.exchange_ipc(dist, capi.ipc_get_handle(fb5.ptr))
             ptrs5 = [fb5.ptr if r == rank else capi.ipc_open(handles[r]) for r in range(world)]
@@ -709,14 +712,14 @@ def run_ours(args, rank, world, local_rank):
             local5 = torch.from_numpy(r5.bits().view(np.int32)).cuda()
             parts = sharding.allgather_words(dist, local5, (n5 + 31) // 32)
             want5 = torch.cat(parts).cpu().numpy().view(np.uint32)
-            got5 = np.zeros(sharding.total_words(1 << 28), np.uint32)
+            got5 = np.zeros(sharding.total_words(c5_total), np.uint32)
             fb5.download(got5)
             ok5 = bool(np.array_equal(got5, want5[:len(got5)]))
             del local5, parts, want5, got5
         alg5 = n5 * 96.25
         also["c5_strong"] = {
-            "objects_total": 1 << 28, "objects_per_gpu": n5, "scaling": "strong", "ms_per_step": ms5,
-            "objects_per_s": (1 << 28) / (ms5 / 1000.0),
+            "objects_total": c5_total, "objects_per_gpu": n5, "scaling": "strong", "ms_per_step": ms5,
+            "objects_per_s": c5_total / (ms5 / 1000.0),
             "kernel": "%s<1>" % capi.KERNEL_NAMES.get(ctx5.get_option(capi.OPT_LAST_KERNEL), "?"), "avg_launch_ms": k5_ms / max(k5_n, 1),
             "frac_of_hbm_peak": alg5 / (k5_ms / max(k5_n, 1) / 1000.0) / 1e9 / peak,
             "bitset_allgather": g5, "bitset_allgather_verified_against_nccl_all_gather": ok5,

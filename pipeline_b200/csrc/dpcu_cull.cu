@@ -393,6 +393,10 @@ namespace dpcu
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
     args.lineWords = ctx->optLineWords ? uint32_t( ctx->optLineWords ) : 32u;
+    // A resident warp that only sees four or five whole lines leaves a ragged tail (each line is 32 sequential steps):
+    // half lines fill it in.  32 Mi objects, one view: 0.518 -> 0.508 ms (this is the per-GPU share of BASELINE C5 on 8 GPUs,
+    // where peer bitsets make this kernel the only choice); at 64 Mi objects whole lines are as fast and store 128 bytes.
+    if ( !ctx->optLineWords && NV == 1 && divUp( divUp( ctx->n, 32 ), 32 ) < size_t( ctx->smCount ) * 48u * 6u ) args.lineWords = 16u;
     const bool useLines  = !ctx->optFma && ( ( peers && !leaf ) || ctx->optKernel == DPCU_KERNEL_LINES || ctx->optKernel == DPCU_KERNEL_LINES_PAIRS || autoLines );
     // several views: the pair-filter form with the queued exact passes (kernel_lines_mv.cuh), unless the earlier form is asked for
     const bool useLinesMv = useLines && !leaf && NV >= 2 && ctx->optKernel != DPCU_KERNEL_LINES;
