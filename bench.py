@@ -492,6 +492,27 @@ def run_ours(args, rank, world, local_rank):
                               "serialise the two (measured: +7 us per step at 1 Mi objects), so the timed steps run without them" % K)
     k_each = ctx.kernel_times()                                  # per-launch device time of the cull kernel (CUDA events)
     ctx.set_option(capi.OPT_PROFILE, 1 if profile_in_timed else 0)
+    cold_read = None
+    if flush is not None and tree is None:
+        # what a launch of this size can reach at all: a plain streaming read of the same number of bytes (nothing computed,
+        # nothing written), same flush protocol, same event bracket - launch latency, ramp-up and the first DRAM round trips
+        # are in it just as they are in the cull kernel's time; the copy peak of MEASURED_PEAKS.json is a large-transfer figure
+        rb = capi.Buffer(int(n_per * 96))
+        rb.fill(3)
+        evr = [(capi.Event(), capi.Event()) for _ in range(K)]
+        for f in range(K):
+            flush.fill(f & 0xFF, stream)
+            capi.read_sweep(sweep.ptr, 256 << 20, stream)
+            evr[f][0].record(stream)
+            capi.read_sweep(rb.ptr, int(n_per * 96), stream)
+            evr[f][1].record(stream)
+        stream.sync()
+        tr = np.array([x.elapsed_ms(y) for x, y in evr])
+        cold_read = {"bytes": int(n_per * 96), "ms_median": float(np.median(tr)), "ms_min": float(tr.min()),
+                     "GBps": n_per * 96 / float(np.median(tr)) / 1e6,
+                     "what": "readSweepKernel (grid-stride 16-byte loads, result discarded) over the same number of bytes the cull reads, "
+                             "cold clean L2, one event pair per launch: the floor for ANY single launch of this size on this GPU"}
+        rb.close()
     k_ms, k_n = float(k_each.sum()), len(k_each)
     changed = [r.changed_count() for r in results]
 
@@ -601,6 +622,9 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n),
                 "launch_ms_p10_p50_p90": [float(x) for x in np.percentile(k_each, [10, 50, 90])] if len(k_each) else None,
                 "step_share": k_ms / ms_total if ms_total else None, "kernel_time_source": kernel_time_source}
+    if cold_read is not None:
+        roofline["cold_read_floor"] = cold_read
+        roofline["frac_of_cold_read_floor"] = cold_read["ms_median"] / k_avg_ms if k_avg_ms else None
     if tree is not None:
         upper = sum(C3_LEVELS[:-1])
         alg_upper = upper * 136.0 + (1 + sum(C3_LEVELS[:-2])) * 64.0     # levels 0..2: K1 launches
@@ -762,6 +786,27 @@ def run_ours(args, rank, world, local_rank):
         for r in res6:
             r.close()
 
+    # ---------------- the other single-GPU BASELINE configurations next to the headline (N = 1 only): the same bench, one
+    # child process per workload (its own context, its own flush protocol), summarised here so that the record of the
+    # default command carries every named configuration; the full lines are what `bench.py --workload c2|c3` prints
+    if args.workload == "c4-single" and world == 1 and not args.no_also and not args.no_children:
+        import subprocess
+        for wl in ("c2", "c3"):
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--no-also", "--no-cpu-baseline",
+                                      "--steps", "20", "--warmup", "5"], capture_output=True, text=True, timeout=300)
+                child = json.loads(out.stdout.strip().splitlines()[-1])
+                cr = child["roofline"]
+                also[wl] = {"config": {k: child["config"][k] for k in ("workload", "objects_total", "views", "matrices", "l2")},
+                            "ms_per_step": child["ms_per_step"], "objects_per_s": child["value"],
+                            "e2e_ms_per_step": child["e2e"]["ms_per_step"], "e2e_objects_per_s": child["e2e"]["value"],
+                            "gpu_launches": child["gpu_launches"], "steps": child["steps"],
+                            "roofline": {k: cr.get(k) for k in ("kernel", "achieved", "peak", "frac", "avg_launch_ms", "step_share", "traffic",
+                                                                "algorithmic_bytes_per_launch", "step_frac", "kernel_time_source",
+                                                                "cold_read_floor", "frac_of_cold_read_floor") if k in cr}}
+            except Exception as e:                   # noqa: BLE001 - the headline line must not depend on the extras
+                also[wl] = {"failed": "%s: %s" % (type(e).__name__, e)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -809,6 +854,7 @@ def main():
     ap.add_argument("--workload", default="c4-single", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra measurements over the same scene (six views, c5 strong, K4, FMA report)")
+    ap.add_argument("--no-children", action="store_true", help="skip also.c2 / also.c3 (child runs of the other single-GPU workloads)")
     ap.add_argument("--no-c5", action="store_true", help="skip also.c5_strong (256 Mi objects over the N GPUs)")
     ap.add_argument("--gather", default="also", choices=["also", "fused", "none"],
                     help="N>1: bitset all-gather through peer stores in the cull kernel's epilogue: measured next to the "

@@ -274,7 +274,7 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* used by the tests to measure the slack of the proof                           */
 #define DPCU_CULL_OPT_LINE_WORDS   10   /* line-granular kernel: bitset words per warp; 0 (default) = 32 (a 128-byte */
                                         /* line); 8 / 16 = shorter lines (more warps on small groups; experiment)    */
-#define DPCU_CULL_OPT_LIST_OFFSETS 11   /* one thread per object forms (direct, views): who turns flipped bits into list offsets  */
+#define DPCU_CULL_OPT_LIST_OFFSETS 11   /* one thread per object forms (direct, views, fused leaf): who turns flipped bits into list offsets */
                                         /* 0 (default) = AUTO; 1 = the cull kernel counts flips per 8192-object segment and its   */
                                         /* last CTA scans the counters; 2 = no counters at all, every compaction CTA popcounts    */
                                         /* the flipped-bit words before its segment (groups <= 2 Mi objects); 3 = counters, every */

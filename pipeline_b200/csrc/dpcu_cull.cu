@@ -439,7 +439,7 @@ namespace dpcu
     // one thread per object forms on small groups: all list bookkeeping moves into the compaction kernel (DPCU_CULL_OPT_SCAN_SEGS)
     // (DPCU_CULL_OPT_LIST_OFFSETS; *listOffsets = 1: last-CTA scan, 2: compaction popcounts words, 3: compaction sums counters)
     *listOffsets = 1;
-    if ( !useFused && !useLines && !useGrid && !useStaged && ctx->optChanged )
+    if ( !useLines && !useGrid && !useStaged && ctx->optChanged )
     {
       int want = ctx->optListOffsets ? ctx->optListOffsets : kAutoListOffsets;
       if ( want == 2 && args.nSegs > 256u ) want = 3;

@@ -154,7 +154,7 @@ namespace dpcu
       if ( lane < NV && ( i - lane ) < a.n ) storeWord<NV>( a.out[lane], a, word, myWord, oldBits );
       ent = entN; entN = entNN; dirty = dirtyN;
     }
-    if ( a.buildChanged ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
+    if ( a.buildChanged && a.countSegs == 1 ) scanSegmentsInLastCta<NV>( a.out, a.nSegs, a.done );
   }
 
   // counts objects whose transform index is not the node of the level entry with the same index

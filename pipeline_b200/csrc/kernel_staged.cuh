@@ -39,7 +39,7 @@ namespace dpcu
     {
       const uint32_t c = old ^ nw;
       o.chg[word] = c;
-      if ( c ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
+      if ( c && a.countSegs ) atomicAdd( o.seg + ( word >> ( kSegObjectsLog2 - 5 ) ), __popc( c ) );
     }
   }
 

@@ -1,11 +1,10 @@
 #!/bin/bash
-export DPCU_BENCH_C5_TOTAL=67108864
-for lw in 0 32; do
-  DPCU_BENCH_LINE_WORDS=$([ $lw = 0 ] && echo "" || echo $lw) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/t_n2_lw$lw.json 2> gpurun_out/t_n2_lw$lw.err
-  python - <<PY
+python tools/stream_floor.py
+timeout 900 python -m pytest tests -x -q -m gpu -k "fused or tree or c3 or leaf" 2>&1 | tail -2
+(time python bench.py > gpurun_out/t_bench.json 2> gpurun_out/t_bench.err) 2>&1 | grep real
+python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/t_n2_lw$lw.json").read().strip().splitlines()[-1])
-c=d["also"]["c5_strong"]
-print("line words $lw: c5(64Mi total over 2) step %.4f ms kernel %.4f ms frac %.3f verified %s | headline %.4f ms gather %s" % (c["ms_per_step"], c["avg_launch_ms"], c["frac_of_hbm_peak"], c["bitset_allgather_verified_against_nccl_all_gather"], d["ms_per_step"], d["also"].get("with_bitset_allgather",{}).get("ms_per_step")))
+d=json.loads(open("gpurun_out/t_bench.json").read().strip().splitlines()[-1])
+r=d["roofline"]; print("%s step %.4f ms value %.2f G e2e %.4f ms kernel %s %.4f frac %.3f share %.2f launches %s" % (d["config"]["workload"], d["ms_per_step"], d["value"]/1e9, d["e2e"]["ms_per_step"], r["kernel"], r["avg_launch_ms"], r["frac"], r["step_share"], d["gpu_launches"]))
+for k,v in d.get("also",{}).items(): print("   also",k,json.dumps({kk:vv for kk,vv in v.items() if kk in ("ms_per_step","ms","frac_of_hbm_peak","disagreements","e2e_ms_per_step","roofline","failed")})[:400])
 PY
-done

@@ -10,7 +10,7 @@ done
 timeout 900 python bench.py --impl reference --steps 3 --warmup 3 > $O/r02_bench_reference_arm.json 2> $O/r02_bench_reference_arm.err; echo "reference arm exit $?"
 # launch list of the default command (cold-cache, serialised: compare shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_bench.csv \
-   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-c5 > $O/r02_launches_bench.log 2>&1; echo "launch list exit $?"
+   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-c5 --no-children > $O/r02_launches_bench.log 2>&1; echo "launch list exit $?"
 cap() {   # name kernel-regex skip workload objects views
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o $O/$1 -f \
      python bench.py --workload $4 --steps 2 --warmup 3 --no-cpu-baseline --no-also > $O/$1.log 2>&1; echo "capture $1 exit $?"

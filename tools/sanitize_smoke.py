@@ -23,10 +23,13 @@ def main():
     launches = 0
     for nv in (1, 2, 6, 8):
         want = [port.cull_bits(lower4, extent4, tidx, mats.reshape(-1), cams[v]) for v in range(nv)]
-        for kernel, fuse_list in ((0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (4, 0), (7, 1), (7, 0), (8, 1)):
+        # (kernel form, list built in the line-granular kernel?, DPCU_CULL_OPT_LIST_OFFSETS of the one thread per object forms)
+        for kernel, fuse_list, offsets in ((0, 1, 0), (1, 1, 0), (1, 1, 1), (1, 1, 2), (2, 1, 0), (3, 1, 0), (3, 1, 1), (3, 1, 2), (4, 1, 0),
+                                           (4, 0, 0), (7, 1, 0), (7, 0, 0), (8, 1, 0)):
             ctx = capi.Cull(0)
             ctx.set_option(capi.OPT_KERNEL, kernel)
             ctx.set_option(capi.OPT_FUSE_LIST, fuse_list)
+            ctx.set_option(capi.OPT_LIST_OFFSETS, offsets)
             ctx.set_objects(lower4, extent4, tidx)
             ctx.set_matrices(mats.reshape(-1))
             res = [ctx.result_create() for _ in range(nv)]
