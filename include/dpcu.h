@@ -158,7 +158,8 @@ int dpcuCullSetMatrices(dpcuCull *ctx, const void *matrices, size_t count, size_
 int dpcuCullUpdateMatrices(dpcuCull *ctx, const uint32_t *indices, size_t n, const void *matrices,
                            size_t strideBytes, int memspace);
 /* Zero-copy feed: cull straight out of a device matrix array owned by someone else (SURVEY.md
- * section 7 hard part 4).  64-byte stride.  The memory must stay valid until the context is
+ * section 7 hard part 4).  64-byte stride, 32-byte aligned (the kernels read a matrix as two
+ * 256-bit loads; anything cudaMalloc returns is).  The memory must stay valid until the context is
  * rebound, given its own copy, or destroyed.  ORDERING IS THE CALLER'S: whatever writes these
  * matrices must be ordered before every dpcuCullRun that reads them, and after the previous one,
  * by running on the same stream or through events (dpcuStreamWaitEvent).  For the world matrices

@@ -108,6 +108,22 @@ namespace dpcu
   }
 
   // 16-byte streaming loads: the object / matrix streams are read exactly once per cull
+  // A 64-byte matrix as two 256-bit loads (sm_100: LDG.E.256) instead of four 128-bit ones.  A warp's matrix rows lie
+  // 64 bytes apart, so every 128-byte line serves two lanes whatever the access size: the four row loads were 64 L1
+  // wavefronts per warp and step, these are 32 - the L1 data pipe was 63 % busy in the six-view kernel (ncu) - and each
+  // load is exactly one 32-byte sector.  Needs 32-byte aligned matrices (dpcuCullBindMatrices checks; own copies are).
+  __device__ __forceinline__ void ldMatrix( float4 const *m, float4 &m0, float4 &m1, float4 &m2, float4 &m3 )
+  {
+#ifdef DPCU_NO_LD256       // A/B builds only (make variant)
+    m0 = __ldg( m ); m1 = __ldg( m + 1 ); m2 = __ldg( m + 2 ); m3 = __ldg( m + 3 );
+    return;
+#endif
+    asm volatile( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                  : "=f"( m0.x ), "=f"( m0.y ), "=f"( m0.z ), "=f"( m0.w ), "=f"( m1.x ), "=f"( m1.y ), "=f"( m1.z ), "=f"( m1.w ) : "l"( m ) );
+    asm volatile( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                  : "=f"( m2.x ), "=f"( m2.y ), "=f"( m2.z ), "=f"( m2.w ), "=f"( m3.x ), "=f"( m3.y ), "=f"( m3.z ), "=f"( m3.w ) : "l"( m + 2 ) );
+  }
+
   __device__ __forceinline__ float4 ldStream( float4 const *p )
   {
     float4 r;

@@ -794,7 +794,7 @@ extern "C"
   {
     DPCU_REQUIRE( ctx, "ctx is NULL" );
     DPCU_REQUIRE( deviceMatrices || !count, "deviceMatrices is NULL" );
-    DPCU_REQUIRE( ( reinterpret_cast<uintptr_t>( deviceMatrices ) & 15 ) == 0, "matrices must be 16-byte aligned" );
+    DPCU_REQUIRE( ( reinterpret_cast<uintptr_t>( deviceMatrices ) & 31 ) == 0, "matrices must be 32-byte aligned (the kernels read them with 256-bit loads)" );
     DPCU_REQUIRE( count < ( size_t( 1 ) << 32 ), "matrix count must fit 32 bits" );
     ctx->boundMats = static_cast<float const *>( deviceMatrices );
     ctx->boundTree = nullptr;

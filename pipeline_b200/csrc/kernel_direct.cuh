@@ -33,10 +33,8 @@ namespace dpcu
         const float4 lo = ldStream( a.lowerIdx + i );
         const float4 ex = ldStream( a.extent + i );
         float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
-        const float4 m0 = __ldg( m + 0 );
-        const float4 m1 = __ldg( m + 1 );
-        const float4 m2 = __ldg( m + 2 );
-        const float4 m3 = __ldg( m + 3 );
+        float4 m0, m1, m2, m3;
+        ldMatrix( m, m0, m1, m2, m3 );
         const Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
 #pragma unroll
         for ( int v = 0; v < NV; ++v )

@@ -85,7 +85,8 @@ namespace dpcu
         float4       *wn = t.world + 4ull * node0;
         float4 const *pw = t.world + 4ull * ent.x;
         const float4 r0 = ldStream( ln + lane ), r1 = ldStream( ln + 32 + lane ), r2 = ldStream( ln + 64 + lane ), r3 = ldStream( ln + 96 + lane );
-        const float4 p0 = __ldg( pw + 0 ), p1 = __ldg( pw + 1 ), p2 = __ldg( pw + 2 ), p3 = __ldg( pw + 3 );
+        float4 p0, p1, p2, p3;
+        ldMatrix( pw, p0, p1, p2, p3 );
         const uint32_t oj = lane >> 2, rj = lane & 3u;          // row j*32+lane belongs to node j*8+oj, row rj
         bufIn[swizzledRow( oj, rj )]      = r0;
         bufIn[swizzledRow( 8 + oj, rj )]  = r1;
@@ -117,8 +118,10 @@ namespace dpcu
         {
           float4 const *ln = t.local + 4ull * ent.y;
           float4 const *pw = t.world + 4ull * ent.x;
-          const float4 l0 = __ldg( ln + 0 ), l1 = __ldg( ln + 1 ), l2 = __ldg( ln + 2 ), l3 = __ldg( ln + 3 );
-          const float4 p0 = __ldg( pw + 0 ), p1 = __ldg( pw + 1 ), p2 = __ldg( pw + 2 ), p3 = __ldg( pw + 3 );
+          float4 l0, l1, l2, l3;
+          ldMatrix( ln, l0, l1, l2, l3 );
+          float4 p0, p1, p2, p3;
+          ldMatrix( pw, p0, p1, p2, p3 );
           w0 = vecMulMat( l0, p0, p1, p2, p3 );                     // Tree.cpp:157, Matmnt.h:1381-1415
           w1 = vecMulMat( l1, p0, p1, p2, p3 );
           w2 = vecMulMat( l2, p0, p1, p2, p3 );

@@ -95,7 +95,7 @@ namespace dpcu
       if ( tile0 + 1 < tile1 ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
       float4 const *m = a.mats + 4ull * idxNext;
       nLo = ldStream( a.lowerIdx + i0 ); nEx = ldStream( a.extent + i0 );
-      nM0 = __ldg( m + 0 ); nM1 = __ldg( m + 1 ); nM2 = __ldg( m + 2 ); nM3 = __ldg( m + 3 );
+      ldMatrix( m, nM0, nM1, nM2, nM3 );
       idxNext = idxNext2;
     }
 #pragma unroll 1
@@ -116,7 +116,7 @@ namespace dpcu
           const uint32_t i1 = min( i + kCullThreads, a.n - 1u );
           float4 const *m = a.mats + 4ull * idxNext;
           nLo = ldStream( a.lowerIdx + i1 ); nEx = ldStream( a.extent + i1 );
-          nM0 = __ldg( m + 0 ); nM1 = __ldg( m + 1 ); nM2 = __ldg( m + 2 ); nM3 = __ldg( m + 3 );
+          ldMatrix( m, nM0, nM1, nM2, nM3 );
         }
         if ( tile + 2 < tile1 ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 2u * kCullThreads, a.n - 1u ) ) + 3 );
       }
@@ -127,10 +127,7 @@ namespace dpcu
         lo = ldStream( a.lowerIdx + ic );
         ex = ldStream( a.extent + ic );
         float4 const *m = a.mats + 4ull * idxNext;
-        m0 = __ldg( m + 0 );
-        m1 = __ldg( m + 1 );
-        m2 = __ldg( m + 2 );
-        m3 = __ldg( m + 3 );
+        ldMatrix( m, m0, m1, m2, m3 );
         if ( tile + 1 < tile1 ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + kCullThreads, a.n - 1u ) ) + 3 );
       }
       const Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );

@@ -19,7 +19,8 @@
 //     go out together: one DRAM round trip per step instead of two dependent ones (object -> its matrix).
 //
 // Measured on the way and NOT in this file any more (64 Mi objects x 6 views, this form: 1.245 ms):
-// L2 prefetch of the next steps, per lane (prefetch.global.L2) or by the TMA unit (cp.async.bulk.prefetch.L2, SASS
+// L2 prefetch of the next steps with ONE prefetch per matrix (half of its sectors, see the step loop; the full-sector form
+// is in for up to four views), per lane (prefetch.global.L2) or by the TMA unit (cp.async.bulk.prefetch.L2, SASS
 // UBLKPF) 1.25 - 1.47 ms; the next step's loads staged in shared memory with cp.async (LDGSTS) at 3 CTAs per SM 1.57 ms
 // (long_scoreboard 6.0 -> 2.6 but the MIO queue saturates: short_scoreboard 0.9 -> 3.2); all six loads a step ahead in
 // registers 1.94 ms (spills), also with the OBB parked in shared memory during the classification; 3 / 5 CTAs per SM
@@ -28,6 +29,9 @@
 
 namespace dpcu
 {
+#ifndef DPCU_MV_PREFETCH_MAX_VIEWS
+#define DPCU_MV_PREFETCH_MAX_VIEWS 4     // up to this many views the next step's sectors are prefetched into L2 (see the step loop)
+#endif
 #ifndef DPCU_MV_MIN_CTAS
 #define DPCU_MV_MIN_CTAS 4          // 64 registers, 32 warps per SM, 45 KB of shared memory per CTA
 #endif
@@ -105,6 +109,19 @@ namespace dpcu
         const uint32_t i0 = min( ( word0 << 5 ) + lane, a.n - 1u );
         idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i0 ) + 3 );
       }
+      // Up to four views the step leaves issue slots free and the kernel waits on DRAM: every 32-byte sector of the NEXT
+      // step's matrices and extents is then asked for a step ahead (prefetch.global.L2 fetches ONE sector - a single
+      // prefetch per matrix, as tried before, covered half of it and the L2 hit rate stayed at 36 %), with the index that
+      // names the matrices running two steps ahead.  64 Mi objects, 2 / 3 / 4 views: 1.012 / 1.049 / 1.079 -> 0.985 / 1.024 /
+      // 1.054 ms; with 5 / 6 views the extra instructions cost more than the shorter waits give (1.170 / 1.232 -> 1.177 /
+      // 1.255 ms), so those keep the plain form.
+      constexpr bool kPrefetch = NV <= DPCU_MV_PREFETCH_MAX_VIEWS;
+      uint32_t idxNext2 = 0;
+      if ( kPrefetch )
+      {
+        const uint32_t i1 = min( ( word0 << 5 ) + lane + 32u, a.n - 1u );
+        idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
+      }
 #pragma unroll 1
       for ( uint32_t w = 0; w < steps; ++w )
       {
@@ -117,11 +134,22 @@ namespace dpcu
         const float4 lo = ldStream( a.lowerIdx + ic );
         const float4 ex = ldStream( a.extent + ic );
         float4 const *m = a.mats + 4ull * tidx;
-        const float4 m0 = __ldg( m + 0 );
-        const float4 m1 = __ldg( m + 1 );
-        const float4 m2 = __ldg( m + 2 );
-        const float4 m3 = __ldg( m + 3 );
-        if ( w + 1 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 32u, a.n - 1u ) ) + 3 );
+        float4 m0, m1, m2, m3;
+        ldMatrix( m, m0, m1, m2, m3 );
+        if ( kPrefetch )
+        {
+          // (the index load two steps ahead also pulls in that step's lowerIdx sectors)
+          if ( w + 1 < steps )
+          {
+            float4 const *mn = a.mats + 4ull * idxNext2;
+            prefetchL2( mn );
+            prefetchL2( mn + 2 );
+            if ( ( lane & 1u ) == 0 ) prefetchL2( a.extent + min( i + 32u, a.n - 1u ) );
+          }
+          idxNext = idxNext2;
+          if ( w + 2 < steps ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 64u, a.n - 1u ) ) + 3 );
+        }
+        else if ( w + 1 < steps ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 32u, a.n - 1u ) ) + 3 );
         Obb obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
         const ObbBall ball = makeBall( obb, a.filterHalf );
         // All views in one straight-line block (the three pair classifications interleave freely), each lane

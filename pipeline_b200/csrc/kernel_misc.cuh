@@ -348,7 +348,9 @@ namespace dpcu
       const float4 lo = ldStream( lowerIdx + i );
       const float4 ex = ldStream( extent + i );
       float4 const *m = mats + 4ull * __float_as_uint( lo.w );
-      const Obb o = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, __ldg( m ), __ldg( m + 1 ), __ldg( m + 2 ), __ldg( m + 3 ) );
+      float4 m0, m1, m2, m3;
+      ldMatrix( m, m0, m1, m2, m3 );
+      const Obb o = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
       const float4 v0 = o.pt;
       const float4 v1 = add4( v0, o.ax );
       const float4 v2 = add4( v0, o.ay );

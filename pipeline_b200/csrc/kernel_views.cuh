@@ -33,8 +33,12 @@ namespace dpcu
     // long_scoreboard 2.05 warps per issue).  The transform index of this thread's object two tiles
     // ahead is fetched now (one register; it also pulls that tile's lowerIdx lines in), the index
     // fetched a tile ago turns into an L2 prefetch of the next tile's matrix and extent lines.
+    // (Only for long runs of tiles per CTA: on the small groups AUTO gives this kernel now - below 2.6 - 7 M objects -
+    // the look-ahead costs more than it hides: 1 Mi x 6 views 44.0 -> 42.0 us, 2 Mi x 3 views 54.2 -> 52.2 us without.)
     const uint32_t strideObjects = gridDim.x * kCullThreads;
+    const bool     ahead = a.nTiles >= 32u * gridDim.x;
     uint32_t idxNext = 0;
+    if ( ahead )
     {
       const uint32_t i1 = blockIdx.x * kCullThreads + threadIdx.x + strideObjects;
       if ( i1 < a.n && i1 >= strideObjects ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
@@ -48,6 +52,7 @@ namespace dpcu
       const uint32_t word     = i >> 5;
 #if DPCU_VIEWS_PREFETCH
       uint32_t idxNext2 = 0;
+      if ( ahead )
       {
         const uint32_t i1 = i + strideObjects, i2 = i1 + strideObjects;
         if ( i2 < a.n && i2 > i1 ) idxNext2 = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i2 ) + 3 );
@@ -69,10 +74,8 @@ namespace dpcu
         const float4 lo = ldStream( a.lowerIdx + i );
         const float4 ex = ldStream( a.extent + i );
         float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
-        const float4 m0 = __ldg( m + 0 );
-        const float4 m1 = __ldg( m + 1 );
-        const float4 m2 = __ldg( m + 2 );
-        const float4 m3 = __ldg( m + 3 );
+        float4 m0, m1, m2, m3;
+        ldMatrix( m, m0, m1, m2, m3 );
         obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
       }
       const bool affine = !live || ( obb.pt.w == 1.0f && obb.ax.w == 0.0f && obb.ay.w == 0.0f && obb.az.w == 0.0f );
