@@ -124,6 +124,15 @@ namespace dpcu
                   : "=f"( m2.x ), "=f"( m2.y ), "=f"( m2.z ), "=f"( m2.w ), "=f"( m3.x ), "=f"( m3.y ), "=f"( m3.z ), "=f"( m3.w ) : "l"( m + 2 ) );
   }
 
+  // ... and the store side (STG.E.256): a 64-byte matrix as two full 32-byte sectors
+  __device__ __forceinline__ void stMatrix( float4 *m, float4 const &m0, float4 const &m1, float4 const &m2, float4 const &m3 )
+  {
+    asm volatile( "st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                  :: "l"( m ), "f"( m0.x ), "f"( m0.y ), "f"( m0.z ), "f"( m0.w ), "f"( m1.x ), "f"( m1.y ), "f"( m1.z ), "f"( m1.w ) : "memory" );
+    asm volatile( "st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                  :: "l"( m + 2 ), "f"( m2.x ), "f"( m2.y ), "f"( m2.z ), "f"( m2.w ), "f"( m3.x ), "f"( m3.y ), "f"( m3.z ), "f"( m3.w ) : "memory" );
+  }
+
   __device__ __forceinline__ float4 ldStream( float4 const *p )
   {
     float4 r;

@@ -126,7 +126,7 @@ namespace dpcu
           w1 = vecMulMat( l1, p0, p1, p2, p3 );
           w2 = vecMulMat( l2, p0, p1, p2, p3 );
           w3 = vecMulMat( l3, p0, p1, p2, p3 );
-          wn[0] = w0; wn[1] = w1; wn[2] = w2; wn[3] = w3;
+          stMatrix( wn, w0, w1, w2, w3 );
           atomicOr( t.dirtyWorld + ( ent.y >> 5 ), 1u << ( ent.y & 31u ) );   // Tree.cpp:158
         }
         else
