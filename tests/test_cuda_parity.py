@@ -493,6 +493,20 @@ def test_error_behaviour(capi):
     with pytest.raises(capi.DpcuError):
         ctx.close()                                     # results still alive
     assert r.is_visible(5) and r.is_visible(10 ** 6)    # never culled / beyond size: visible (ResultBitSet.h:69-76)
+    # borrowed matrices are read with 256-bit loads: a 16-byte aligned pointer is refused, a 32-byte aligned one works
+    buf = capi.Buffer(100 * 64 + 64)
+    buf.upload(np.concatenate([np.zeros(8, np.float32), mats.reshape(-1), np.zeros(8, np.float32)]))
+    with pytest.raises(capi.DpcuError) as e:
+        ctx.bind_matrices(buf.ptr + 16, 100)
+    assert "32-byte" in str(e.value)
+    ctx.bind_matrices(buf.ptr + 32, 100)
+    ctx.run([r], scenes.camera_c2())
+    want = ctx.result_create()
+    ctx.set_matrices(mats.reshape(-1))
+    ctx.run([want], scenes.camera_c2())
+    assert np.array_equal(r.bits(), want.bits())
+    want.close()
+    buf.close()
     r.close()
     ctx.close()
 
