@@ -18,7 +18,10 @@
 //
 // One cull = ONE launch of the line-granular kernel for large groups (bitset lines, peer / host-mirror
 // stores and the ordered changed list in one pass), otherwise cull kernel (ballot -> word, XOR with the
-// previous word, popc into the segment counters, last CTA scans them) -> compaction kernel.
+// previous word, popc into the segment counters) -> compaction kernel, launched as a programmatic dependent of
+// the cull kernel: each of its CTAs sums the counters before its segment (groups beyond 32 Mi objects: the cull
+// kernel's last CTA scans them instead), expands its segment's flipped bits into the list and stores the
+// segment's part of a host mirror (DPCU_CULL_OPT_LIST_OFFSETS).
 // The kernels live in kernel_*.cuh (arguments, direct, views, staged, lines, fused leaf, misc), their
 // arithmetic in cull_math.cuh / cull_views.cuh / cull_filter.cuh; this file is the host side.
 //

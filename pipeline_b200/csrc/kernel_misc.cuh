@@ -4,10 +4,11 @@
 namespace dpcu
 {
   // ------------------------------------------------------------------------------------------
-  // Ordered changed list.  One CTA per 8192-object segment and view: seg[] already holds the
-  // exclusive prefix, so the CTA only block-scans the popcounts of its 256 flipped-bit words and
-  // expands them; ascending group index order falls out of the layout (BitArray::traverseBits
-  // order, dp/util/BitArray.h:127-136).
+  // Ordered changed list.  One CTA per 8192-object segment and view: the number of changes before
+  // the segment comes from prefix[] (written by the cull kernel's last CTA), from the segment counters
+  // (summed here) or from the flipped-bit words themselves (popcounted here) - CompactArgs::selfPrefix -
+  // then the CTA block-scans the popcounts of its 256 flipped-bit words and expands them; ascending
+  // group index order falls out of the layout (BitArray::traverseBits order, dp/util/BitArray.h:127-136).
   struct CompactArgs
   {
     uint32_t const *chg[DPCU_MAX_VIEWS];
