@@ -31,8 +31,18 @@ def one_round(port, rng, log):
     lower4, extent4, upper4, mats, tidx = cases.random_case(cap, seed=seed)
     if rng.randint(3) == 0:                                   # shared / permuted transforms
         tidx = rng.randint(0, cap, size=cap).astype(np.uint32)
+    if rng.randint(4) == 0:                                   # nasty values: non-affine rows, NaN / Inf, denormals, corners on planes
+        sl, se, su, sm, st, svps = cases.special_case(min(cap, 4096), seed=seed & 0xFFFF)
+        where = rng.choice(cap, size=len(sl), replace=False)
+        mats = mats.copy()
+        lower4, extent4 = lower4.copy(), extent4.copy()
+        mats[where] = sm
+        lower4[where, :3], extent4[where, :3] = sl[:, :3], se[:, :3]
+        special_views = list(svps)
+    else:
+        special_views = []
     flat = mats.reshape(-1)
-    cams = list(scenes.cube_map_cameras((float(rng.uniform(-40, 40)), 0.0, float(rng.uniform(-40, 40))))) + [scenes.camera_c2(), scenes.orbit_camera(int(rng.randint(50)))]
+    cams = special_views + list(scenes.cube_map_cameras((float(rng.uniform(-40, 40)), 0.0, float(rng.uniform(-40, 40))))) + [scenes.camera_c2(), scenes.orbit_camera(int(rng.randint(50)))]
     ctx = capi.Cull(0)
     ctx.set_option(capi.OPT_KERNEL, kernel)
     ctx.set_option(capi.OPT_FUSE_LIST, fuse)
