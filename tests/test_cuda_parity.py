@@ -286,6 +286,26 @@ def test_differential_fuzz_slice(capi, port):
     assert decisions > 0
 
 
+def test_tree_fuzz_slice(capi, port):
+    """A fixed-seed slice of tools/fuzz_tree.py: random hierarchies (ordered / shuffled levels), narrow / wide kernels,
+    dirty sets of every shape, non-finite locals, the last level fused into a cull in half of the rounds; world matrices
+    bit for bit (NaN payloads aside), dirty sets, fused-cull bits and changed lists against the oracle."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_tree", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                            "tools", "fuzz_tree.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    master = np.random.RandomState(20261019)
+    for _ in range(150):
+        seed = int(master.randint(1, 1 << 30))
+        log = []
+        try:
+            fuzz.one_round(port, np.random.RandomState(seed), log.append)
+        except AssertionError as e:
+            raise AssertionError("round seed %d (%s): %s" % (seed, "; ".join(log), e))
+
+
 @pytest.mark.parametrize("nv", [1, 2])
 def test_list_offset_modes_many_segments(capi, port, nv):
     """DPCU_CULL_OPT_LIST_OFFSETS on a group of 3 Mi objects (384 segments): the last-CTA scan, the compaction kernel
