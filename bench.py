@@ -781,7 +781,7 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": ms6, "objects_per_s": n_total / (ms6 / 1000.0), "object_views_per_s": 6 * n_total / (ms6 / 1000.0),
             "kernel": "%s<6>" % capi.KERNEL_NAMES.get(ctx.get_option(capi.OPT_LAST_KERNEL), "?"), "avg_launch_ms": k6_ms / max(k6_n, 1),
             "achieved_GBps": alg6 / (k6_ms / max(k6_n, 1) / 1000.0) / 1e9, "frac_of_hbm_peak": alg6 / (k6_ms / max(k6_n, 1) / 1000.0) / 1e9 / peak,
-            "bound": "hbm (0.81: one exposed DRAM round trip per step at 8 warps per scheduler; provable pairs decided by the "
+            "bound": "hbm (0.82: one exposed DRAM round trip per step at 8 warps per scheduler; provable pairs decided by the "
                      "centre / radius filter two views per instruction, the rest queued for the reference arithmetic; DESIGN.md section 3)",
             "changed_per_step_last": [r.changed_count() for r in res6]}
         for r in res6:
