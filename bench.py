@@ -427,8 +427,9 @@ def run_ours(args, rank, world, local_rank):
         sweep.fill(1)
 
     # per-launch events inside the timed region only where the cull kernel is the step's only launch (large groups); for the
-    # flushed small workloads they would break the dependent launch of the compaction kernel - see kernel_time_source below
-    profile_in_timed = flush is None
+    # flushed small workloads and the tree-fed frame they would sit between the cull kernel and the dependent launches around
+    # it (tree levels before, compaction kernel behind) - see kernel_time_source below
+    profile_in_timed = flush is None and tree is None
     ctx.set_option(capi.OPT_PROFILE, 1 if profile_in_timed else 0)
 
     def step(f, s=stream):
@@ -483,13 +484,14 @@ def run_ours(args, rank, world, local_rank):
         ctx.set_option(capi.OPT_PROFILE, 1)
         ctx.kernel_time()
         for f in range(K):
-            flush.fill(f & 0xFF, stream)
-            capi.read_sweep(sweep.ptr, 256 << 20, stream)
+            if flush is not None:
+                flush.fill(f & 0xFF, stream)
+                capi.read_sweep(sweep.ptr, 256 << 20, stream)
             step(W + f)
         stream.sync()
-        kernel_time_source = ("CUDA events around every cull-kernel launch in a SEPARATE pass of the same %d steps (same flush protocol) right "
-                              "after the timed region: events between the cull kernel and its programmatic dependent compaction launch "
-                              "serialise the two (measured: +7 us per step at 1 Mi objects), so the timed steps run without them" % K)
+        kernel_time_source = ("CUDA events around every cull-kernel launch in a SEPARATE pass of the same %d steps (same protocol) right "
+                              "after the timed region: events between the cull kernel and the programmatic dependent launches around it "
+                              "serialise them (measured: +7 us per step at 1 Mi objects), so the timed steps run without them" % K)
     k_each = ctx.kernel_times()                                  # per-launch device time of the cull kernel (CUDA events)
     ctx.set_option(capi.OPT_PROFILE, 1 if profile_in_timed else 0)
     cold_read = None

@@ -508,8 +508,17 @@ namespace dpcu
     }
     if ( useFused )
     {
-      cullFusedLeafKernel<NV><<<grid, kCullThreads, 0, stream>>>( args, *leaf );
-      DPCU_CUDA( cudaGetLastError() );
+      // behind the tree's upper levels on the same stream: a programmatic dependent launch like theirs (dpcu_tree.cu)
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.stream = stream;
+      cfg.gridDim = dim3( unsigned( grid ) );
+      cfg.blockDim = dim3( kCullThreads );
+      DPCU_CUDA( cudaLaunchKernelEx( &cfg, cullFusedLeafKernel<NV>, args, *leaf ) );
     }
     else if ( useLines )
     {

@@ -34,6 +34,9 @@ namespace dpcu
                                                             float4 const *__restrict__ local, float4 *world,
                                                             uint32_t const *__restrict__ dirtyLocal, uint32_t *dirtyWorld )
   {
+    // launched as a programmatic dependent of the previous level (treeComputeLevels): its CTAs are placed while that
+    // level drains, and everything it reads of it is read behind this point
+    cudaGridDependencySynchronize();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t e = t >> 2, r = t & 3u;
     if ( e >= count ) return;
@@ -55,6 +58,7 @@ namespace dpcu
                                                                         uint32_t const *dirtyLocal, uint32_t *dirtyWorld )
   {
     __shared__ float4 sTranspose[kWideThreads / 32][2][128];     // per warp: locals in, worlds out (2 KiB each)
+    cudaGridDependencySynchronize();                             // see treeLevelKernel
     const uint32_t lane   = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * kWideThreads;
     float4 *bufIn = sTranspose[threadIdx.x >> 5][0], *bufOut = sTranspose[threadIdx.x >> 5][1];
@@ -195,17 +199,30 @@ namespace dpcu
       float4 *world = static_cast<float4 *>( t->world.ptr );
       uint32_t const *dirtyLocal = static_cast<uint32_t const *>( t->dirtyLocal.ptr );
       uint32_t *dirtyWorld = static_cast<uint32_t *>( t->dirtyWorld.ptr );
+      // Levels are a chain of small dependent launches (C3: 4096, 65 536 and 1 Mi nodes before the fused leaf level): each
+      // is launched with programmatic stream serialization, so its CTAs are placed while the level before drains and wait
+      // in cudaGridDependencySynchronize() - the launch latency of a level is off the frame's critical path.
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.stream = s;
       if ( count >= t->wideMinNodes )
       {
         size_t grid = divUp( size_t( count ), size_t( kWideThreads ) );
         size_t cap  = size_t( t->smCount ) * t->wideCtasPerSm;
-        treeLevelWideKernel<<<unsigned( grid < cap ? grid : cap ), kWideThreads, 0, s>>>( entries, count, local, world, dirtyLocal, dirtyWorld );
+        cfg.gridDim  = dim3( unsigned( grid < cap ? grid : cap ) );
+        cfg.blockDim = dim3( kWideThreads );
+        DPCU_CUDA( cudaLaunchKernelEx( &cfg, treeLevelWideKernel, entries, count, local, world, dirtyLocal, dirtyWorld ) );
       }
       else
       {
-        treeLevelKernel<<<unsigned( divUp( size_t( count ) * 4, 256 ) ), 256, 0, s>>>( entries, count, local, world, dirtyLocal, dirtyWorld );
+        cfg.gridDim  = dim3( unsigned( divUp( size_t( count ) * 4, 256 ) ) );
+        cfg.blockDim = dim3( 256 );
+        DPCU_CUDA( cudaLaunchKernelEx( &cfg, treeLevelKernel, entries, count, local, world, dirtyLocal, dirtyWorld ) );
       }
-      DPCU_CUDA( cudaGetLastError() );
       ++t->launches;
     }
     return DPCU_OK;

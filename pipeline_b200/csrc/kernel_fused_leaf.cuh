@@ -39,6 +39,9 @@ namespace dpcu
     __shared__ f32x2 sP[NV > 1 ? NV * 8 : 1];
     __shared__ FilterScratch<NV> sScratch[NV > 1 ? kCullThreads / 32 : 1];
     if ( NV > 1 ) fillViewTable<NV>( sP, a );
+    // launched as a programmatic dependent of the tree's last upper level (dpcuCullRunWithTree): everything read of it
+    // (parents' world matrices, dirty bits) is read behind this point
+    cudaGridDependencySynchronize();
     const uint32_t lane   = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * kCullThreads;
     float4 *bufIn = sTranspose[threadIdx.x >> 5][0], *bufOut = sTranspose[threadIdx.x >> 5][1];
