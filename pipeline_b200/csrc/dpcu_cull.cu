@@ -439,7 +439,7 @@ namespace dpcu
     const bool useChains = ctx->optKernel == DPCU_KERNEL_VIEWS_CHAINS;
     const bool useViews  = !useFused && !useLines && !useGrid && !ctx->optFma && ( ctx->optKernel == DPCU_KERNEL_VIEWS || useChains || ( ctx->optKernel == DPCU_KERNEL_AUTO && NV >= 2 ) );
     args.chunkCounter = results[0]->donePtr() + 1;
-    // one thread per object forms on small groups: all list bookkeeping moves into the compaction kernel (DPCU_CULL_OPT_SCAN_SEGS)
+    // one thread per object forms (direct, views, fused leaf): who turns the flipped bits into list offsets
     // (DPCU_CULL_OPT_LIST_OFFSETS; *listOffsets = 1: last-CTA scan, 2: compaction popcounts words, 3: compaction sums counters)
     *listOffsets = 1;
     if ( !useLines && !useGrid && !useStaged && ctx->optChanged )

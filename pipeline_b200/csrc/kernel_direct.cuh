@@ -4,7 +4,8 @@
 namespace dpcu
 {
   // ------------------------------------------------------------------------------------------
-  // K2, direct variant: one thread per object, six 16-byte loads, persistent grid-stride tiles.
+  // K2, direct variant: one thread per object, two 16-byte loads (AABB, index) and two 256-bit loads (its matrix),
+  // persistent grid-stride tiles.
   template <int NV>
   __global__ void __launch_bounds__( kCullThreads )
   DPCU_KERNEL_NAME( cullDirectKernel )( const __grid_constant__ CullArgs<NV> a )

@@ -48,17 +48,36 @@ namespace dpcu
     if ( a.hostBits[v] && w < a.nWords ) a.hostBits[v][w] = __ldcg( a.bits[v] + w );
     const uint32_t pc = __popc( c );
     uint32_t base0, count;
-    if ( a.selfPrefix == 2 )
+    if ( a.selfPrefix )
     {
-      // The cull kernel counted flips per segment (fire-and-forget atomics) and stopped there: no fence, no ticket, no
-      // serial scan by its last CTA.  This CTA sums the counters before its own - one L2 round trip for up to 1024
-      // segments - and the last CTA to have read them zeroes them for the next cull.
-      uint32_t *seg = a.seg[v];
+      // prefix[] holds nothing yet: this CTA finds the number of flips before its segment (`before`, summed over the
+      // threads below) and in it (`mine`) itself.
       uint32_t before = 0, mine = 0;
-      for ( uint32_t k = threadIdx.x; k <= s; k += 256 )
+      if ( a.selfPrefix == 2 )
       {
-        const uint32_t x = __ldcg( seg + k );
-        if ( k < s ) before += x; else mine = x;
+        // The cull kernel counted flips per segment (fire-and-forget atomics) and stopped there: no fence, no ticket, no
+        // serial scan by its last CTA.  This CTA sums the counters before its own - one L2 round trip for up to 4096
+        // segments, 16 loads per thread at most.
+        uint32_t const *seg = a.seg[v];
+        for ( uint32_t k = threadIdx.x; k <= s; k += 256 )
+        {
+          const uint32_t x = __ldcg( seg + k );
+          if ( k < s ) before += x; else mine = x;
+        }
+      }
+      else
+      {
+        // The cull kernel kept no counters at all (groups of at most 256 segments): the flips before this segment are the
+        // popcount of s KiB of flipped-bit words, read from L2 as 16-byte vectors.
+        uint4 const *q = reinterpret_cast<uint4 const *>( a.chg[v] );
+        const uint32_t nVec = s * ( kSegWords / 4 );
+#pragma unroll 16
+        for ( uint32_t k = threadIdx.x; k < nVec; k += 256 )
+        {
+          const uint4 x = __ldcg( q + k );
+          before += __popc( x.x ) + __popc( x.y ) + __popc( x.z ) + __popc( x.w );
+        }
+        mine = pc;
       }
 #pragma unroll
       for ( int d = 16; d > 0; d >>= 1 )
@@ -74,59 +93,25 @@ namespace dpcu
       __syncthreads();                               // sWarp is reused by the scan below
       if ( threadIdx.x == 0 )
       {
-        a.prefix[v][s] = base0;
+        a.prefix[v][s] = base0;                      // what the other consumers of the result read (count = prefix[nSegs])
         if ( s == a.nSegs - 1 )
         {
           a.prefix[v][a.nSegs] = base0 + count;
           if ( a.hostCount[v] ) *a.hostCount[v] = base0 + count;
         }
       }
-      // every thread's counter reads are complete (their values went through the barrier above)
-      __shared__ uint32_t sLast;
-      if ( threadIdx.x == 0 ) sLast = ( atomicAdd( a.done, 1u ) == gridDim.x * gridDim.y - 1 ) ? 1u : 0u;
-      __syncthreads();
-      if ( sLast )
+      if ( a.selfPrefix == 2 )
       {
-        for ( uint32_t vv = 0; vv < gridDim.y; ++vv )
-          for ( uint32_t k = threadIdx.x; k < a.nSegs; k += 256 ) a.seg[vv][k] = 0u;
-        if ( threadIdx.x == 0 ) *a.done = 0u;
-      }
-    }
-    else if ( a.selfPrefix )
-    {
-      // Small groups (DPCU_CULL_OPT_SCAN_SEGS): the cull kernel kept no counters.  The flips before this segment are
-      // the popcount of s KiB of flipped-bit words, read from L2 as 16-byte vectors (<= 255 KiB, a microsecond); in
-      // exchange the cull kernel loses its atomics, its fence and the last-CTA scan, which were 4 us of a 27 us kernel
-      // at 1 Mi objects.
-      uint4 const *q = reinterpret_cast<uint4 const *>( a.chg[v] );
-      const uint32_t nVec = s * ( kSegWords / 4 );
-      uint32_t before = 0;
-#pragma unroll 16
-      for ( uint32_t k = threadIdx.x; k < nVec; k += 256 )
-      {
-        const uint4 x = __ldcg( q + k );
-        before += __popc( x.x ) + __popc( x.y ) + __popc( x.z ) + __popc( x.w );
-      }
-      uint32_t mine = pc;
-#pragma unroll
-      for ( int d = 16; d > 0; d >>= 1 )
-      {
-        before += __shfl_xor_sync( 0xffffffffu, before, d );
-        mine   += __shfl_xor_sync( 0xffffffffu, mine, d );
-      }
-      if ( lane == 0 ) { sBefore[warp] = before; sWarp[warp] = mine; }
-      __syncthreads();
-      base0 = 0; count = 0;
-#pragma unroll
-      for ( int k = 0; k < 8; ++k ) { base0 += sBefore[k]; count += sWarp[k]; }
-      __syncthreads();                               // sWarp is reused by the scan below
-      if ( threadIdx.x == 0 )
-      {
-        a.prefix[v][s] = base0;
-        if ( s == a.nSegs - 1 )
+        // the last CTA to have read the counters (every thread's reads went through the barriers above) zeroes them, and
+        // the ticket, for the next cull
+        __shared__ uint32_t sLast;
+        if ( threadIdx.x == 0 ) sLast = ( atomicAdd( a.done, 1u ) == gridDim.x * gridDim.y - 1 ) ? 1u : 0u;
+        __syncthreads();
+        if ( sLast )
         {
-          a.prefix[v][a.nSegs] = base0 + count;
-          if ( a.hostCount[v] ) *a.hostCount[v] = base0 + count;
+          for ( uint32_t vv = 0; vv < gridDim.y; ++vv )
+            for ( uint32_t k = threadIdx.x; k < a.nSegs; k += 256 ) a.seg[vv][k] = 0u;
+          if ( threadIdx.x == 0 ) *a.done = 0u;
         }
       }
     }
