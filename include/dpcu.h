@@ -243,7 +243,7 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
 /* Tuning / reporting knobs (never change results unless stated). */
 #define DPCU_CULL_OPT_KERNEL        1   /* DPCU_KERNEL_*: which exact form of the cull kernel runs           */
 #define DPCU_KERNEL_AUTO    0           /* the measured winner: line-granular (list built in-kernel) for groups */
-                                        /* of >= 43.6 M (1 view) / 7.0 M (2) / 3.6 M (3) / 3.0 M (4) / 2.6 M (5+ views) objects and when peer */
+                                        /* of >= 6.7 M (1 view) / 7.0 M (2) / 3.6 M (3) / 3.0 M (4) / 2.6 M (5+ views) objects and when peer */
                                         /* bitsets are set; else direct                                         */
                                         /* (1 view) / view-sequential packed (>= 2 views)                       */
 #define DPCU_KERNEL_DIRECT  1           /* one thread per object, scalar arithmetic, all views interleaved   */
@@ -281,6 +281,12 @@ int dpcuCullGetBoundingBox(dpcuCull *ctx, float *out6);
                                         /* the flipped-bit words before its segment (groups <= 2 Mi objects); 3 = counters, every */
                                         /* compaction CTA sums the counters before its segment (groups <= 32 Mi objects; no fence, */
                                         /* ticket or serial scan at the end of the cull kernel).  Larger groups fall back to 1     */
+#define DPCU_CULL_OPT_L2_PREFETCH  12   /* 1 (default) = the line-granular kernels (1 view; 2-4 views) ask for every sector of the   */
+                                        /* next step's matrices and extents a step ahead (prefetch.global.L2): 3 % faster per cull  */
+                                        /* (64 Mi objects: 0.985 vs 1.014 ms; without the prefetch, index look-ahead only: 0.998 ms). */
+                                        /* 0 = for callers that cull back to back for hundreds of milliseconds: under the board's     */
+                                        /* power cap the extra L2 lookups cost more than they give (median of 300 culls: 1.059 ms    */
+                                        /* with, 1.026 ms without, 1.049 ms for the round-1 kernel)                                   */
 #define DPCU_CULL_OPT_LAST_KERNEL   8   /* read-only: DPCU_KERNEL_* form the last cull ran                          */
 int dpcuCullSetOption(dpcuCull *ctx, int option, int value);
 int dpcuCullGetOption(const dpcuCull *ctx, int option, int *value);

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DPCU_LIB") or os.path.join(HERE, "lib", "libdpcu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF, OPT_FUSE_LIST, OPT_LAST_KERNEL, OPT_FILTER, OPT_LINE_WORDS, OPT_LIST_OFFSETS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+OPT_KERNEL, OPT_FMA, OPT_CHANGED_LIST, OPT_CTAS_PER_SM, OPT_PROFILE, OPT_FUSE_LEAF, OPT_FUSE_LIST, OPT_LAST_KERNEL, OPT_FILTER, OPT_LINE_WORDS, OPT_LIST_OFFSETS, OPT_L2_PREFETCH = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
 TREE_OPT_WIDE_MIN_NODES = 1
 KERNEL_NAMES = {1: "cullDirectKernel", 2: "cullStagedKernel", 3: "cullViewsKernel", 4: "cullLinesKernel", 5: "cullViewsKernel", 6: "cullFusedLeafKernel",
                 7: "cullLinesMvKernel", 8: "cullGridKernel"}

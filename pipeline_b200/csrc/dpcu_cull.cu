@@ -134,7 +134,7 @@ struct dpcuCull
   bool         maxIndexKnown = true;
   bool         maxIndexStale = false;    // objects were overwritten / removed since the running maximum was started
   dpcu::StreamFence stagingFree;         // the last upload out of `staging` (the next user waits for it, not the caller)
-  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1, optLineWords = 0, optListOffsets = 0;
+  int          optKernel = 0, optFma = 0, optChanged = 1, optCtasPerSm = 0, optProfile = 0, optFuseLeaf = 1, optFuseList = 1, optFilter = 1, optLineWords = 0, optListOffsets = 0, optL2Prefetch = 1;
   int          lastKernel = 0;           // DPCU_KERNEL_* of the last cull launched (DPCU_CULL_OPT_LAST_KERNEL)
   uint64_t     objectsVersion = 0;       // bumped whenever objects are (re)uploaded
   dpcuTree    *leafTree = nullptr;       // cached answer of the leaf-binding check of dpcuCullRunWithTree
@@ -356,6 +356,7 @@ namespace dpcu
     }
     args.useFilter = ( NV > 1 && ctx->optFilter ) ? 1 : 0;
     args.nMats      = uint32_t( ctx->nMats );
+    args.l2Prefetch = ctx->optL2Prefetch;
     args.filterHalf = 0.5f;
     if ( NV > 1 )
     {
@@ -391,7 +392,9 @@ namespace dpcu
     // compaction: 6 views 2 Mi 79 vs 75 us, 3 Mi 97 vs 104 us; 4 views 3 Mi 83 vs 83 us, 4 Mi 97 vs 108 us; 3 views 3 Mi 79 vs
     // 75 us, 4 Mi 93 vs 95 us; 2 views 6 Mi 130 vs 120 us, 8 Mi 146 vs 155 us; 1 view 24 Mi 398 vs 388 us, 32 Mi 519 vs 515 us,
     // 40 Mi 641 vs 642 us, 64 Mi 1.011 vs 1.013 ms)
-    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 6u * 48u : NV == 2 ? 46u : NV == 3 ? 24u : NV == 4 ? 20u : 17u );
+    // (one view again, after the line-granular kernel got its index look-ahead and full-sector L2 prefetch: lines vs direct +
+    // compaction 4 Mi 85 vs 77 us, 8 Mi 140 vs 146 us, 16 Mi 252 vs 264 us, 32 Mi 480 vs 509 us, 64 Mi 0.979 vs 1.013 ms)
+    const size_t wantedLines = size_t( ctx->smCount ) * ( NV == 1 ? 44u : NV == 2 ? 46u : NV == 3 ? 24u : NV == 4 ? 20u : 17u );
     const bool bigEnough = divUp( divUp( ctx->n, 32 ), 32 ) >= wantedLines;
     const bool autoLines = ctx->optKernel == DPCU_KERNEL_AUTO && !leaf && bigEnough
                         && ( mirrors || ( ctx->optChanged && ctx->optFuseList ) );
@@ -1419,6 +1422,7 @@ extern "C"
       case DPCU_CULL_OPT_LINE_WORDS:   DPCU_REQUIRE( value == 0 || value == 8 || value == 16 || value == 32, "line words must be 0 (auto), 8, 16 or 32" );
                                        ctx->optLineWords = value; break;
       case DPCU_CULL_OPT_LIST_OFFSETS: DPCU_REQUIRE( value >= 0 && value <= 3, "list offsets must be 0..3" ); ctx->optListOffsets = value; break;
+      case DPCU_CULL_OPT_L2_PREFETCH:  ctx->optL2Prefetch = value ? 1 : 0; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullSetOption: unknown option %d", option );
     }
     return DPCU_OK;
@@ -1440,6 +1444,7 @@ extern "C"
       case DPCU_CULL_OPT_FILTER:       *value = ctx->optFilter; break;
       case DPCU_CULL_OPT_LINE_WORDS:   *value = ctx->optLineWords; break;
       case DPCU_CULL_OPT_LIST_OFFSETS: *value = ctx->optListOffsets; break;
+      case DPCU_CULL_OPT_L2_PREFETCH:  *value = ctx->optL2Prefetch; break;
       default: return dpcu::fail( DPCU_ERR_INVALID_VALUE, "dpcuCullGetOption: unknown option %d", option );
     }
     return DPCU_OK;

@@ -48,6 +48,7 @@ namespace dpcu
     uint32_t      lineWords; // line-granular kernel: bitset words per warp (32 = one 128-byte line; 8 for mid-size groups)
     int           useFilter; // cull_filter.cuh: decide provable (object, view) pairs from centre and radius
     uint32_t      nMats;     // matrices behind `mats` (bounds the speculative matrix prefetch of kernel_lines_mv.cuh)
+    int           l2Prefetch; // line-granular kernels (1 view, 2-4 views): ask for the next step's sectors a step ahead (DPCU_CULL_OPT_L2_PREFETCH)
     ViewOut       out[NV];
     float4        vp[NV][4];
     ViewFilter    filter[NV];

@@ -146,7 +146,10 @@ namespace dpcu
   // 6 views 2.068 ms at 3 CTAs (80 registers) -> 1.937 ms at 4 (64 registers, ~70 bytes of spills); the 2-view
   // instantiation is close to the HBM bound and prefers no spills: 1.154 ms at 4 CTAs, 1.103 ms at 3, 1.289 ms at 5
   template <int NV, bool kFuseList>
-  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? 6 : ( NV == 2 ? 3 : 4 ) )
+#ifndef DPCU_LINES1_MIN_CTAS
+#define DPCU_LINES1_MIN_CTAS 5     // 47 registers without spills once the two look-ahead indices are live (6 CTAs: 40 registers, spills, no gain)
+#endif
+  __global__ void __launch_bounds__( kCullThreads, NV == 1 ? DPCU_LINES1_MIN_CTAS : ( NV == 2 ? 3 : 4 ) )
   cullLinesKernel( const __grid_constant__ CullArgs<NV> a )
   {
     const uint32_t lane   = threadIdx.x & 31u;
@@ -190,6 +193,20 @@ namespace dpcu
         const uint32_t i1 = ( ( word0 + 1u ) << 5 ) + lane;
         if ( i1 < a.n ) idxNext = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + i1 ) + 3 );
       }
+#ifndef DPCU_LINES1_AHEAD
+#define DPCU_LINES1_AHEAD 1
+#endif
+      // One view (round 2): the scheme of the pair-filter kernel (kernel_lines_mv.cuh).  The transform index of THIS step
+      // was fetched a step ago, so the step's loads go out together (one DRAM round trip instead of object -> matrix), and
+      // the index of the NEXT step - fetched two steps ahead - turns into an L2 prefetch of every 32-byte sector of that
+      // step's matrices and extents.
+      constexpr bool kAhead1 = NV == 1 && DPCU_LINES1_AHEAD;
+      uint32_t idxThis = 0, idxAfter = 0;
+      if ( kAhead1 )
+      {
+        idxThis  = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( ( word0 << 5 ) + lane, a.n - 1u ) ) + 3 );
+        idxAfter = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( ( word0 << 5 ) + lane + 32u, a.n - 1u ) ) + 3 );
+      }
 #pragma unroll 1      // measured: one step in flight at 48 warps per SM beats unroll 2 / 4 at lower occupancy
       for ( uint32_t w = 0; w < steps; ++w )
       {
@@ -208,14 +225,26 @@ namespace dpcu
         }
         Obb obb;
         obb.pt = obb.ax = obb.ay = obb.az = make_float4( 0.f, 0.f, 0.f, 0.f );
+        if ( kAhead1 && a.l2Prefetch && w + 1u < steps )               // DPCU_CULL_OPT_L2_PREFETCH
+        {
+          float4 const *mn = a.mats + 4ull * idxAfter;
+          prefetchL2( mn );
+          prefetchL2( mn + 2 );
+          if ( ( lane & 1u ) == 0 ) prefetchL2( a.extent + min( i + 32u, a.n - 1u ) );
+        }
         if ( live )
         {
           const float4 lo = ldStream( a.lowerIdx + i );
           const float4 ex = ldStream( a.extent + i );
-          float4 const *m = a.mats + 4ull * __float_as_uint( lo.w );
+          float4 const *m = a.mats + 4ull * ( kAhead1 ? idxThis : __float_as_uint( lo.w ) );
           float4 m0, m1, m2, m3;
           ldMatrix( m, m0, m1, m2, m3 );
           obb = makeObb( lo.x, lo.y, lo.z, ex.x, ex.y, ex.z, m0, m1, m2, m3 );
+        }
+        if ( kAhead1 )
+        {
+          idxThis = idxAfter;
+          if ( w + 2u < steps ) idxAfter = __ldg( reinterpret_cast<uint32_t const *>( a.lowerIdx + min( i + 64u, a.n - 1u ) ) + 3 );
         }
         if ( NV == 1 )
         {

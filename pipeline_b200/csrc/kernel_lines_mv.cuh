@@ -139,7 +139,7 @@ namespace dpcu
         if ( kPrefetch )
         {
           // (the index load two steps ahead also pulls in that step's lowerIdx sectors)
-          if ( w + 1 < steps )
+          if ( w + 1 < steps && a.l2Prefetch )                    // DPCU_CULL_OPT_L2_PREFETCH
           {
             float4 const *mn = a.mats + 4ull * idxNext2;
             prefetchL2( mn );

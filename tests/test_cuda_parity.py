@@ -264,6 +264,35 @@ def test_view_counts_both_kernels(capi, port, kernel, nv):
     _check_views(capi, port, kernel, lower4, extent4, tidx, mats, _views_for(nv), frames=2)
 
 
+@pytest.mark.parametrize("nv", [1, 2, 4])
+def test_l2_prefetch_option_changes_nothing(capi, port, nv):
+    """DPCU_CULL_OPT_L2_PREFETCH: the line-granular kernels with and without the look-ahead prefetch produce the oracle's bits
+    and lists (ragged size: the prefetch addresses of the last steps are clamped to the last object)."""
+    n = 100003
+    lower4, extent4, upper4, mats, tidx = cases.random_case(n, seed=5)
+    flat = mats.reshape(-1)
+    vps = _views_for(nv)
+    for pf in (1, 0):
+        ctx = capi.Cull(0)
+        ctx.set_option(capi.OPT_KERNEL, capi.KERNEL_LINES if nv == 1 else capi.KERNEL_LINES_PAIRS)
+        ctx.set_option(capi.OPT_L2_PREFETCH, pf)
+        assert ctx.get_option(capi.OPT_L2_PREFETCH) == pf
+        ctx.set_objects(lower4, extent4, tidx)
+        ctx.set_matrices(flat)
+        res = [ctx.result_create() for _ in range(nv)]
+        state = [port.result_resize(np.zeros(0, np.uint32), 0, n) for _ in range(nv)]
+        for f in range(2):
+            use = vps if f == 0 else vps[::-1].copy()
+            ctx.run(res, use)
+            for v in range(nv):
+                want = port.cull_bits(lower4, extent4, tidx, flat, use[v])
+                assert np.array_equal(res[v].bits(), want), (pf, f, v)
+                assert np.array_equal(res[v].changed(), port.update_changed(want, state[v], n)), (pf, f, v)
+        for r in res:
+            r.close()
+        ctx.close()
+
+
 def test_differential_fuzz_slice(capi, port):
     """A fixed-seed slice of tools/fuzz_forms.py: random sizes, view counts, kernel forms, list-offset modes, line sizes,
     host mirrors, object-count changes and live edits between frames, every frame compared with the oracle.  (The tool

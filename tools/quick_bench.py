@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--changed", type=int, default=1)
     ap.add_argument("--filter", type=int, default=1, help="multi-view filter (DPCU_CULL_OPT_FILTER)")
     ap.add_argument("--line-words", type=int, default=0, help="DPCU_CULL_OPT_LINE_WORDS")
+    ap.add_argument("--l2-prefetch", type=int, default=1, help="DPCU_CULL_OPT_L2_PREFETCH")
     ap.add_argument("--list-offsets", type=int, default=0, help="DPCU_CULL_OPT_LIST_OFFSETS")
     ap.add_argument("--profile", type=int, default=1, help="0: no per-launch events (they sit between the cull and the dependent compaction launch)")
     ap.add_argument("--static", type=int, default=0, help="1: same camera every iteration")
@@ -43,6 +44,7 @@ def main():
     ctx.set_option(capi.OPT_FILTER, a.filter)
     ctx.set_option(capi.OPT_LIST_OFFSETS, a.list_offsets)
     ctx.set_option(capi.OPT_LINE_WORDS, a.line_words)
+    ctx.set_option(capi.OPT_L2_PREFETCH, a.l2_prefetch)
     res = [ctx.result_create() for _ in range(a.views)]
     cams = np.concatenate([scenes.cube_map_cameras(), scenes.cube_map_cameras((50.0, 20.0, -30.0))]) if a.views > 1 else None
     s = capi.Stream()
