@@ -94,3 +94,25 @@ def test_product_does_not_link_the_oracle(libpath):
                 txt = open(os.path.join(root, f), errors="replace").read()
                 for b in banned:
                     assert b not in txt, "%s references %s: the product path must not use the oracle" % (f, b)
+
+
+def test_python_constants_follow_the_header():
+    """capi.py's DPCU_CULL_OPT_* / DPCU_KERNEL_* numbers are the header's (the harness must not drift from the ABI)."""
+    import re
+    from pipeline_b200 import capi
+    text = open(HEADER).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(DPCU_[A-Z0-9_]+)\s+(\d+)\b", text)}
+    pairs = {"DPCU_CULL_OPT_KERNEL": capi.OPT_KERNEL, "DPCU_CULL_OPT_FMA": capi.OPT_FMA, "DPCU_CULL_OPT_CHANGED_LIST": capi.OPT_CHANGED_LIST,
+             "DPCU_CULL_OPT_CTAS_PER_SM": capi.OPT_CTAS_PER_SM, "DPCU_CULL_OPT_PROFILE": capi.OPT_PROFILE,
+             "DPCU_CULL_OPT_FUSE_LEAF": capi.OPT_FUSE_LEAF, "DPCU_CULL_OPT_FUSE_LIST": capi.OPT_FUSE_LIST,
+             "DPCU_CULL_OPT_LAST_KERNEL": capi.OPT_LAST_KERNEL, "DPCU_CULL_OPT_FILTER": capi.OPT_FILTER,
+             "DPCU_CULL_OPT_LINE_WORDS": capi.OPT_LINE_WORDS, "DPCU_CULL_OPT_LIST_OFFSETS": capi.OPT_LIST_OFFSETS,
+             "DPCU_CULL_OPT_L2_PREFETCH": capi.OPT_L2_PREFETCH,
+             "DPCU_KERNEL_AUTO": capi.KERNEL_AUTO, "DPCU_KERNEL_DIRECT": capi.KERNEL_DIRECT, "DPCU_KERNEL_STAGED": capi.KERNEL_STAGED,
+             "DPCU_KERNEL_VIEWS": capi.KERNEL_VIEWS, "DPCU_KERNEL_LINES": capi.KERNEL_LINES,
+             "DPCU_KERNEL_VIEWS_CHAINS": capi.KERNEL_VIEWS_CHAINS, "DPCU_KERNEL_FUSED_LEAF": capi.KERNEL_FUSED_LEAF,
+             "DPCU_KERNEL_LINES_PAIRS": capi.KERNEL_LINES_PAIRS, "DPCU_KERNEL_GRID": capi.KERNEL_GRID}
+    for name, value in pairs.items():
+        assert defs.get(name) == value, (name, defs.get(name), value)
+    options = sorted(v for k, v in defs.items() if k.startswith("DPCU_CULL_OPT_"))
+    assert options == list(range(1, len(options) + 1)), "option numbers must be dense and unique: %s" % options

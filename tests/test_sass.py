@@ -179,3 +179,29 @@ def test_staged_kernel_uses_tma_bulk_copies(sass):
         assert "UBLKCP" in text, name + ": no bulk TMA copy (cp.async.bulk)"
         assert "SYNCS" in text, name + ": no mbarrier"
         assert "LDGSTS" in text, name + ": no cp.async gather"
+
+
+def test_gathered_matrices_are_read_with_256_bit_loads(sass):
+    """every gather-by-index matrix read is two LDG.E.256 (ld.global.nc.v8.f32), not four 128-bit row
+    loads - half the L1 wavefronts of a warp whose matrices lie 64 bytes apart."""
+    for family in ("cullDirectKernel", "cullLinesKernel", "cullLinesMvKernel", "cullViewsKernel", "cullFusedLeafKernel"):
+        kernels = {n: b for n, b in _kernels(sass, family).items() if "_fma" not in n}
+        assert kernels, family
+        for name, body in kernels.items():
+            wide = [i for i in body if re.search(r"\bLDG\.E\.[A-Z0-9.]*256", i)]
+            assert len(wide) >= 2, name + ": no 256-bit matrix loads"
+
+
+def test_line_granular_kernels_prefetch_full_sectors(sass):
+    """The single-view line-granular kernel and the pair-filter kernel up to four views look ahead: at least three L2
+    prefetches per step (two sectors of the next matrix, one of the extents); five and more views keep the plain form."""
+    def prefetches(body):
+        return sum(1 for i in body if re.search(r"\bCCTL\.[A-Z0-9.]*PF2|\bPREFETCH|CCTL\.E\.PF2", i))
+    one = [b for n, b in _kernels(sass, "cullLinesKernel").items() if "ILi1E" in n]
+    assert one and all(prefetches(b) >= 3 for b in one)
+    for name, body in _kernels(sass, "cullLinesMvKernel").items():
+        nv = int(re.search(r"ILi(\d)E", name).group(1))
+        if nv <= 4:
+            assert prefetches(body) >= 3, name
+        else:
+            assert prefetches(body) == 0, name
